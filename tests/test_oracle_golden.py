@@ -1,0 +1,286 @@
+"""Pin the CPU oracle against the reference's own known answers and against
+fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+
+import argparse
+import math
+
+import numpy as np
+import pytest
+
+from oracle import golem_oracle as go
+from oracle import truth
+
+
+# ---------------------------------------------------------------- docstring KATs
+def test_kat_determinant():
+    # golemflavor/fr.py:69-74
+    m = [[-1.65238188 - 0.59549718j, 0.27486548 - 0.18437467j, -1.35524534 - 0.38542072j],
+         [-1.07480906 + 0.29630449j, -0.47808456 - 0.80316821j, -0.88609356 - 1.50737308j],
+         [-0.14924144 - 0.99230446j, 0.49504234 + 0.63639805j, 2.29258915 - 0.36537507j]]
+    assert abs(go.determinant(m) - (2.7797571563274688 + 3.0841795325804848j)) < 1e-7  # inputs printed to 8 digits
+
+
+def test_kat_angles_to_fr():
+    # golemflavor/fr.py:97-98
+    ref = (0.38340579025361626, 0.16431676725154978, 0.45227744249483393)
+    assert np.allclose(go.angles_to_fr((0.3, 0.4)), ref, rtol=0, atol=1e-15)
+
+
+def test_kat_angles_to_u():
+    # golemflavor/fr.py:131-135
+    ref = np.array([[0.66195018 + 0.j, 0.33097509 + 0.j, 0.04757188 - 0.6708311j],
+                    [-0.34631487 - 0.42427084j, 0.61741198 - 0.21213542j, 0.52331757 + 0.j],
+                    [0.28614067 - 0.42427084j, -0.64749908 - 0.21213542j, 0.52331757 + 0.j]])
+    assert np.abs(go.angles_to_u((0.2, 0.3, 0.5, 1.5)).astype(np.complex128) - ref).max() < 1e-8
+
+
+def test_kat_cardano():
+    # golemflavor/fr.py:186-195
+    ham = np.array([[0.66195018 + 0.j, 0.33097509 + 0.j, 0.04757188 - 0.6708311j],
+                    [-0.34631487 - 0.42427084j, 0.61741198 - 0.21213542j, 0.52331757 + 0.j],
+                    [0.28614067 - 0.42427084j, -0.64749908 - 0.21213542j, 0.52331757 + 0.j]])
+    ref = np.array([[-0.11143379 - 0.58863683j, -0.09067747 - 0.48219068j, 0.34276625 - 0.08686465j],
+                    [0.14835519 + 0.47511473j, -0.18299305 + 0.40777481j, 0.31906300 + 0.82514223j],
+                    [-0.62298966 + 0.07231745j, -0.61407815 - 0.42709603j, 0.03660313 + 0.30160428j]])
+    got = go.cardano_eqn(ham).astype(np.complex128)
+    assert np.abs(got - ref).max() < 5e-8  # 8-digit printed input
+
+
+def test_kat_normalize_fr():
+    # golemflavor/fr.py:254-256
+    assert np.allclose(go.normalize_fr((1, 2, 3)), [1 / 6, 1 / 3, 0.5])
+
+
+def test_kat_params_to_bsmu_and_u_to_fr():
+    # golemflavor/fr.py:354-358 and 519-521
+    ref = np.array([[0.18658169 - 6.34190523e-01j, -0.26460391 + 2.01884200e-01j, 0.67247096 - 9.86808417e-07j],
+                    [-0.50419832 + 2.14420570e-01j, -0.36013768 + 5.44254868e-01j, 0.03700961 + 5.22039894e-01j],
+                    [-0.32561308 - 3.95946524e-01j, 0.64294909 - 2.23453580e-01j, 0.03700830 + 5.22032403e-01j]])
+    got = go.params_to_BSMu((0.2, 0.3, 0.5, 1.5, -20), dim=3, energy=1000)
+    assert np.abs(got.astype(np.complex128) - ref).max() < 1e-8
+    fr = go.u_to_fr((1, 2, 0), got)
+    assert np.allclose(np.asarray(fr, dtype=float), [0.33740075, 0.33176584, 0.33083341], atol=1e-8)
+
+
+def test_kat_unitarity_identity():
+    # golemflavor/fr.py:481-486
+    assert np.array_equal(go.test_unitarity(np.identity(3)), np.identity(3))
+
+
+def test_kat_docs_mappings():
+    # docs/source/physics.rst:277-279 / examples/tutorial.ipynb:165,186-187
+    for src, ref in [((1, 0, 0), (0.55, 0.18, 0.27)), ((0, 1, 0), (0.18, 0.44, 0.38)),
+                     ((1, 2, 0), (0.31, 0.35, 0.34))]:
+        fr = np.asarray(go.u_to_fr(go.normalize_fr(src), go.NUFIT_U), dtype=float)
+        assert np.allclose(fr, ref, atol=5e-3)
+    ang = go.fr_to_angles(go.u_to_fr(go.normalize_fr((1, 0, 0)), go.NUFIT_U))
+    assert abs(float(ang[0]) - 0.54) < 6e-3 and abs(float(ang[1]) - 0.50) < 6e-3  # tutorial.ipynb:401-402
+
+
+# ---------------------------------------------------------------- golden fixtures
+def test_golden_basic(golden):
+    d = golden('ref_basic.npz')
+    u = np.array([go.angles_to_u(a).astype(np.complex128) for a in d['ang']])
+    assert np.abs(u - d['u']).max() < 1e-15
+    ub = go.batch_angles_to_u(d['ang']).astype(np.complex128)
+    assert np.abs(ub - d['u']).max() < 1e-15
+    assert np.abs(go.NUFIT_U.astype(np.complex128) - d['nufit_u']).max() < 1e-16
+    sf = np.array([go.angles_to_fr(a) for a in d['src_ang']])
+    assert np.abs(sf - d['src_fr']).max() == 0
+    assert np.abs(go.batch_angles_to_fr(d['src_ang']) - d['src_fr']).max() < 1e-16
+    back = np.array([[float(x) for x in go.fr_to_angles(f)] for f in d['src_fr']])
+    assert np.allclose(back, d['src_back'], rtol=0, atol=1e-15)
+    fr = np.array([np.asarray(go.u_to_fr(s, go.angles_to_u(a)), dtype=float)
+                   for s, a in zip(d['srcs'], d['ang'])])
+    assert np.abs(fr - d['fr']).max() < 1e-15
+    frb = go.batch_u_to_fr(d['srcs'], go.batch_angles_to_u(d['ang'])).astype(float)
+    assert np.abs(frb - d['fr']).max() < 1e-15
+    v = np.array([go.cardano_eqn(np.array(h, dtype=go.CLD)).astype(np.complex128) for h in d['herm']])
+    assert np.abs(v - d['herm_vecs']).max() < 1e-13
+    vb = go.batch_cardano(d['herm']).astype(np.complex128)
+    assert np.abs(vb - d['herm_vecs']).max() < 1e-13
+
+
+def test_golden_bsm_u(golden):
+    d = golden('ref_bsm_u.npz')
+    worst = 0.0
+    for k in range(len(d['dim'])):
+        sm_u = go.angles_to_u(d['sm'][k])
+        v = go.params_to_BSMu(tuple(d['npang'][k]) + (d['loglam'][k],), int(d['dim'][k]),
+                              d['energy'][k], mass_eigenvalues=list(d['mass'][k]),
+                              sm_u=sm_u, texture='NONE', check_uni=False)
+        fr = np.asarray(go.u_to_fr(d['src'][k], v), dtype=float)
+        f = go.test_unitarity(v)
+        resid = float(max(abs(np.trace(f) - 3), abs(np.sum(f) - 3)))
+        if d['resid'][k] < 1e-9:
+            # well-conditioned for the reference: restatement must agree tightly
+            worst = max(worst, np.abs(fr - d['fr'][k]).max())
+        assert (resid > 1e-7) == (d['resid'][k] > 1e-7)
+    assert worst < 1e-12
+    # textures resolve to the same tuples as golemflavor/fr.py:370-376
+    for k in np.where(d['tex'] != 'NONE')[0][:20]:
+        assert np.array_equal(go.TEXTURE_ANGLES[str(d['tex'][k])], d['npang'][k])
+
+
+class _P:
+    def __init__(self, name, value, ranges, prior=None, std=None, tag=None):
+        self.name, self.value, self.nominal_value = name, value, value
+        self.ranges, self.prior, self.std, self.tag = tuple(ranges), prior, std, tag
+
+
+def _bsm_pset(dim, npang):
+    ps = [_P('s_12_2', 0.307, [0, 1], 'LIMITEDGAUSS', 0.013, 'SM_ANGLES'),
+          _P('c_13_4', (1 - 0.02206) ** 2, [0, 1], 'LIMITEDGAUSS', 0.00147, 'SM_ANGLES'),
+          _P('s_23_2', 0.538, [0, 1], 'LIMITEDGAUSS', 0.069, 'SM_ANGLES'),
+          _P('dcp', 4.08404, [0, 2 * np.pi], None, 2.0, 'SM_ANGLES'),
+          _P('m21_2', 7.40e-23, [6.80e-23, 8.02e-23], 'GAUSSIAN', 2.1e-24, 'SM_ANGLES'),
+          _P('m3x_2', 2.494e-21, [2.399e-21, 2.593e-21], 'GAUSSIAN', 3.3e-23, 'SM_ANGLES')]
+    for k, nm in enumerate(['np_s12', 'np_c13', 'np_s23', 'np_dcp']):
+        ps.append(_P(nm, npang[k], [0, 2 * np.pi], None, 0.2, 'MMANGLES'))
+    b = go.SCALE_BOUNDARIES[dim]
+    ps.append(_P('logLam', np.mean(b), b, None, 3, 'SCALE'))
+    return ps
+
+
+def test_golden_flux(golden):
+    d = golden('ref_flux.npz')
+    n_checked = 0
+    for k in range(0, len(d['dim']), 3):
+        th = list(d['theta'][k])
+        args = argparse.Namespace(binning=d['binning'], source_ratio=go.normalize_fr(d['src'][k]),
+                                  dimension=int(d['dim'][k]), texture='NONE', no_bsm=False)
+        try:
+            fr = np.asarray(go.flux_averaged_BSMu(th, args, -2.0, _bsm_pset(int(d['dim'][k]), th[6:10])),
+                            dtype=float)
+            ok = True
+        except AssertionError:
+            ok = False
+        assert ok == bool(d['ok'][k])
+        if ok:
+            assert np.abs(fr - d['fr'][k]).max() < 1e-11
+            n_checked += 1
+    assert n_checked > 50
+    # fixed-texture route of the oracle == explicit-tuple route of the reference
+    k = int(np.where(d['tex'] == 'OET')[0][0])
+    th = list(d['theta'][k])
+    args = argparse.Namespace(binning=d['binning'], source_ratio=go.normalize_fr(d['src'][k]),
+                              dimension=int(d['dim'][k]), texture='OET', no_bsm=False)
+    ps = [p for p in _bsm_pset(int(d['dim'][k]), th[6:10]) if p.tag != 'MMANGLES']
+    fr = np.asarray(go.flux_averaged_BSMu(th[:6] + th[10:], args, -2.0, ps), dtype=float)
+    assert np.abs(fr - d['fr'][k]).max() < 1e-14
+
+
+def test_batch_flux_matches_reference_and_truth(golden):
+    d = golden('ref_flux.npz')
+    for dim in (3, 6):
+        for src in ((1, 2, 0), (1, 0, 0), (0, 1, 0)):
+            m = (d['dim'] == dim) & np.all(d['src'] == np.array(src, float), axis=1)
+            th = d['theta'][m]
+            fr, resid = go.batch_flux_averaged_fr(th[:, :4], th[:, 4:6], th[:, 6:10], th[:, 10], dim,
+                                                  d['binning'], go.normalize_fr(src))
+            ok = d['ok'][m]
+            assert np.array_equal(resid < 1e-7, ok)
+            # the reference's own Cardano is ill-conditioned where its unitarity residual is
+            # large (it accepts up to 1e-7): compare tightly only on the well-conditioned rows
+            well = ok & (resid < 1e-10)
+            assert np.abs(fr[well] - d['fr'][m][well]).max() < 1e-11
+            assert np.all(np.abs(fr[ok] - d['fr'][m][ok]).max(axis=1) <= 1e-11 + 1e3 * resid[ok])
+            fr_t = truth.eigh_flux_averaged_fr(th[:, :4], th[:, 4:6], th[:, 6:10], th[:, 10], dim,
+                                               d['binning'], go.normalize_fr(src))
+            # LAPACK truth agrees with mpmath everywhere, including where the reference fails
+            assert np.abs(fr_t - d['fr_mp'][m]).max() < 2e-11
+
+
+def _nb_psets(asimov_angles):
+    asimov = [_P('measured_angle1', asimov_angles[0], [0, 1], None, 0.02, 'BESTFIT'),
+              _P('measured_angle2', asimov_angles[1], [-1, 1], None, 0.02, 'BESTFIT')]
+    llh = _bsm_pset(6, (0, 0, 0, 0))[:4] + [
+        _P('source_angle1', 0, [0, 1], None, None, 'SRCANGLES'),
+        _P('source_angle2', 0, [-1, 1], None, None, 'SRCANGLES')]
+    return asimov, llh
+
+
+def test_golden_lnprob_sm(golden):
+    d = golden('ref_llh.npz')
+    asimov, llh = _nb_psets(d['asimov_angles'])
+    args = argparse.Namespace(source_ratio=None)
+    for k in list(range(0, 300, 7)) + [0]:
+        got = go.ln_prob(list(d['theta'][k]), args, asimov, llh)
+        ref = d['lnprob'][k]
+        if np.isfinite(ref):
+            assert abs(got - ref) <= 1e-11 * abs(ref)
+        else:
+            assert got == ref
+    assert abs(d['lnprob'][0] - (-458.6843569885842)) < 1e-9
+    # batch route
+    lo = [p.ranges[0] for p in llh]
+    hi = [p.ranges[1] for p in llh]
+    kind = [2, 2, 2, 0, 0, 0]
+    mu = [p.nominal_value for p in llh]
+    sg = [p.std or 1.0 for p in llh]
+    lp = go.batch_lnprior(d['theta'], lo, hi, kind, mu, sg)
+    fin = np.isfinite(d['lnprior'])
+    assert np.array_equal(np.isfinite(lp), fin)
+    assert np.abs(lp[fin] - d['lnprior'][fin]).max() < 1e-10
+    u = go.batch_angles_to_u(d['theta'][:, :4])
+    with np.errstate(invalid='ignore'):
+        fr = go.batch_u_to_fr(go.batch_angles_to_fr(d['theta'][:, 4:6]), u).astype(float)
+    assert np.nanmax(np.abs(fr[fin] - d['fr'][fin])) < 1e-15
+    bf = go.angles_to_fr(d['asimov_angles'])
+    tot = lp + go.batch_multi_gaussian(fr, bf, 0.02)
+    f2 = np.isfinite(d['lnprob'])
+    assert np.array_equal(np.isfinite(tot), f2)
+    assert np.abs((tot[f2] - d['lnprob'][f2]) / d['lnprob'][f2]).max() < 1e-12
+
+
+def test_golden_lnprior7_and_multigauss(golden):
+    d = golden('ref_llh.npz')
+    ps = [p for p in _bsm_pset(6, (0, 0, 0, 0)) if p.tag != 'MMANGLES']
+    got = np.array([go.lnprior(list(t), ps) for t in d['theta7'][::5]])
+    ref = d['lnprior7'][::5]
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.abs(got[fin] - ref[fin]).max() < 1e-10
+    kind = [2, 2, 2, 0, 1, 1, 0]
+    lp = go.batch_lnprior(d['theta7'], [p.ranges[0] for p in ps], [p.ranges[1] for p in ps], kind,
+                          [p.nominal_value for p in ps], [p.std for p in ps])
+    fin = np.isfinite(d['lnprior7'])
+    assert np.array_equal(np.isfinite(lp), fin)
+    assert np.abs((lp[fin] - d['lnprior7'][fin]) / d['lnprior7'][fin]).max() < 1e-12
+    # the three limited-Gaussian normalisers quoted in SURVEY.md section 8c
+    for p, ref in zip(ps[:3], (3.423867388315928, 5.6035543449868195, 1.7547102411909439)):
+        assert abs(go.truncnorm_lognorm(p.nominal_value, p.std, 0., 1.) - ref) < 1e-12
+
+    assert abs(float(d['mg_spot']) - (-433.2707465833296)) < 1e-10
+    assert abs(go.multi_gaussian([.3, .35, .35], [.55, .18, .27], .02) - float(d['mg_spot'])) < 1e-10
+    mg = go.batch_multi_gaussian(d['mg_fr'], d['mg_bf'], 0.02)
+    fin = np.isfinite(d['mg'])
+    assert np.array_equal(np.isfinite(mg), fin)          # same -inf (pdf underflow) set
+    safe = fin & (d['mg'] + 320 > -700)                  # above the sub-normal band
+    assert np.abs((mg[safe] - d['mg'][safe]) / d['mg'][safe]).max() < 1e-12
+    mgw = go.batch_multi_gaussian(d['mg_fr'], d['mg_bf'], 0.2, offset=0.0)
+    assert np.abs(mgw - d['mg_wide']).max() < 1e-12
+
+
+# ---------------------------------------------------------------- scan support
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+             (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, ref in kats:
+        out = go.philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in out) == ref
+    u = go.philox_uniforms(26, 0, 1000)
+    assert u.min() > 0 and u.max() < 1 and abs(u.mean() - 0.5) < 0.02
+    assert np.array_equal(go.philox_uniforms(26, 500, 10), u[500:510])
+
+
+def test_ternary_histogram_definition():
+    rng = np.random.default_rng(3)
+    frs = rng.dirichlet([1, 1, 1], size=5000)
+    frs[0] = (1.0, 0.0, 0.0)
+    h = go.ternary_histogram(frs, 25)
+    assert h.shape == (26, 26, 26) and h.sum() == 5000
+    assert h[25, 0, 0] >= 1        # x == 1.0 lands in the last bin (np.histogramdd)
