@@ -1,0 +1,186 @@
+/*
+ * gf_model.cuh -- device-side flattening of the reference's ln_prob closure
+ * (`partial(ln_prob, args=..., asimov_paramset=..., llh_paramset=...)`,
+ * scripts/fr.py:182-187) and the per-point evaluation built on gf_physics.cuh.
+ *
+ * gf_dev_model is passed to every kernel BY VALUE as a __grid_constant__ parameter
+ * (constant bank, uniform access, no global symbol => concurrent launches with
+ * different models on different streams are safe).
+ */
+#ifndef GF_MODEL_CUH
+#define GF_MODEL_CUH
+
+#include "../../include/golemflavor_b200.h"
+#include "gf_physics.cuh"
+
+struct gf_dev_model {
+    int32_t ndim, no_bsm, nbins, llh_kind, emulate_underflow, np_free;
+    int32_t col_sm[4], col_mass[2], col_src[2], col_np[4], col_scale, col_x;
+    double fixed_sm[4], fixed_mass[2], fixed_src[3], fixed_np[4], fixed_loglam;
+    gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
+    double g[GF_MAX_BINS];      /* 2 Ec^(dim-2) 2^70: H*2E = H0 + 10^logLam g T          */
+    double width[GF_MAX_BINS];  /* |E_hi - E_lo|                          (fr.py:414)    */
+    double fr_bf[3];
+    double half_inv_s2;         /* 1/(2 sigma^2)                                        */
+    double lognorm3;            /* -1.5 log(2 pi sigma^2)                               */
+    double offset, underflow_logpdf, llh_const, epsilon;
+    double lo[GF_MAX_DIM], hi[GF_MAX_DIM], mu[GF_MAX_DIM], inv_sigma[GF_MAX_DIM], lognorm[GF_MAX_DIM];
+    double cdf_lo[GF_MAX_DIM], cdf_span[GF_MAX_DIM], sigma[GF_MAX_DIM]; /* scans: inverse-CDF draws */
+    int32_t kind[GF_MAX_DIM];
+};
+
+/* strided accessor for theta (see include/golemflavor_b200.h "theta") */
+struct gf_theta_view {
+    const double* p;
+    int64_t ld_point, ld_dim;
+    GF_HD double at(int64_t i, int k) const { return p[i * ld_point + (int64_t)k * ld_dim]; }
+};
+
+/* Physical inputs of one parameter point. */
+struct gf_point {
+    double sm[4], mass[2], np[4], loglam, src[3];
+};
+
+/* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
+template <class Get>
+GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
+    if (m.np_free) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
+    }
+    q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
+    if (m.col_src[0] >= 0) {
+        gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
+    } else if (m.col_x >= 0) {
+        const double x = get(m.col_x); /* scripts/mc_x.py:187: source = (x, 1-x, 0) */
+        q.src[0] = x;
+        q.src[1] = 1.0 - x;
+        q.src[2] = 0.0;
+    } else {
+        q.src[0] = m.fixed_src[0];
+        q.src[1] = m.fixed_src[1];
+        q.src[2] = m.fixed_src[2];
+    }
+}
+
+/*
+ * Measured flavor composition of one point.
+ *   no_bsm : fr = u_to_fr(source, angles_to_u(sm))                (notebook SM model)
+ *   else   : flux_averaged_BSMu -- per energy bin H*2E = H0 + rho_b T, |V|^2, u_to_fr,
+ *            bin-width weighted mean, renormalised                  (fr.py:441-457)
+ * The source normalisation 1/sum(s) and the 1/(E_max-E_min) factor cancel in the final
+ * renormalisation and are not applied per bin.
+ */
+GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
+    unsigned st = 0u;
+    const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
+    double X[9];
+    if (m.no_bsm) {
+        gfp_pmns_abs2(t, X);
+        double f[3];
+        gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
+        const double inv = 1.0 / (q.src[0] + q.src[1] + q.src[2]);
+        fr[0] = f[0] * inv;
+        fr[1] = f[1] * inv;
+        fr[2] = f[2] * inv;
+    } else {
+        const gfp_cols12 u = gfp_cols_from_trig(t);
+        const gfp_herm3 h0 = gfp_herm_from_cols(u, q.mass[0] * GFP_MASS_SCALE, q.mass[1] * GFP_MASS_SCALE);
+        gfp_herm3 T;
+        if (m.np_free) {
+            const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
+            T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
+        } else {
+            T = m.T;
+        }
+#ifdef __CUDA_ARCH__
+        const double lam = exp10(q.loglam);
+#else
+        const double lam = pow(10.0, q.loglam);
+#endif
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        for (int b = 0; b < m.nbins; ++b) {
+            const double rho = lam * m.g[b];
+            gfp_herm3 h;
+            h.d0 = fma(rho, T.d0, h0.d0);
+            h.d1 = fma(rho, T.d1, h0.d1);
+            h.d2 = fma(rho, T.d2, h0.d2);
+            h.ar = fma(rho, T.ar, h0.ar);
+            h.ai = fma(rho, T.ai, h0.ai);
+            h.br = fma(rho, T.br, h0.br);
+            h.bi = fma(rho, T.bi, h0.bi);
+            h.cr = fma(rho, T.cr, h0.cr);
+            h.ci = fma(rho, T.ci, h0.ci);
+            st |= gfp_herm3_abs2(h, X);
+            double f[3];
+            gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
+            const double wd = m.width[b];
+            a0 = fma(wd, f[0], a0);
+            a1 = fma(wd, f[1], a1);
+            a2 = fma(wd, f[2], a2);
+            /* |V|^2 must be a doubly stochastic matrix: a negative entry beyond epsilon is the
+             * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
+            const double mn = fmin(fmin(fmin(X[0], X[1]), fmin(X[2], X[3])), fmin(fmin(X[4], X[5]), fmin(fmin(X[6], X[7]), X[8])));
+            if (!(mn >= -m.epsilon)) st |= GFP_ST_NON_UNITARY;
+        }
+        const double inv = 1.0 / (a0 + a1 + a2);
+        fr[0] = a0 * inv;
+        fr[1] = a1 * inv;
+        fr[2] = a2 * inv;
+    }
+    if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
+    return st;
+}
+
+/* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside. */
+template <class Get>
+GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
+    double lp = 0.0;
+    bool inside = true;
+    for (int k = 0; k < m.ndim; ++k) {
+        const double v = get(k);
+        inside = inside && (v >= m.lo[k]) && (v <= m.hi[k]);
+        if (m.kind[k] != GF_PRIOR_UNIFORM) {
+            const double z = (v - m.mu[k]) * m.inv_sigma[k];
+            lp += fma(-0.5 * z, z, m.lognorm[k]);
+        }
+    }
+    return inside ? lp : -INFINITY;
+}
+
+/* llh.multi_gaussian (llh.py:53-54) in closed form, with the pdf-underflow -> -inf emulation. */
+GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_inv_s2, double lognorm3, double offset,
+                               int emulate_underflow, double underflow_logpdf) {
+    const double d0 = fr[0] - bf[0], d1 = fr[1] - bf[1], d2 = fr[2] - bf[2];
+    const double logpdf = fma(-half_inv_s2, fma(d0, d0, fma(d1, d1, d2 * d2)), lognorm3);
+    if (emulate_underflow && logpdf < underflow_logpdf) return -INFINITY;
+    return logpdf + offset;
+}
+
+/* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
+template <class Get>
+GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
+    const double lp = gf_point_lnprior(m, get);
+    if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
+        fr[0] = fr[1] = fr[2] = NAN;
+        st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;
+        return (lp != lp) ? NAN : -INFINITY;
+    }
+    if (m.llh_kind == GF_LLH_FLAT) {
+        /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
+        gf_point q;
+        gf_resolve_point(m, get, q);
+        st = gf_point_fr(m, q, fr);
+        return lp + m.llh_const;
+    }
+    gf_point q;
+    gf_resolve_point(m, get, q);
+    st = gf_point_fr(m, q, fr);
+    return lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
+}
+
+#endif /* GF_MODEL_CUH */

@@ -1,0 +1,190 @@
+/*
+ * golemflavor_b200 -- C ABI of the B200-native log-posterior hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes and returns
+ * an int status (GF_OK = 0; on error `gf_last_error()` describes it).  Pointers
+ * named `d_*` are DEVICE pointers (cudaMalloc / torch tensors), pointers named
+ * `h_*` are HOST pointers; `stream` is a `cudaStream_t` passed as `void*`
+ * (NULL = the legacy default stream).  Nothing here allocates on the caller's
+ * behalf except the `*_host` convenience calls, which own their staging buffers.
+ * There is NO CPU implementation behind this ABI: without a CUDA device every
+ * compute call returns GF_ERR_CUDA.
+ *
+ * Each function cites the reference interface it replaces
+ * (ShiveshM/GolemFlavor, paths relative to its repository root).
+ *
+ * Layout conventions
+ *   complex matrices : [n][3][3][2] doubles (re, im) == NumPy complex128 C-order
+ *   theta            : element (point i, parameter k) at theta[i*ld_point + k*ld_dim]
+ *                      (row-major emcee layout: ld_point = ndim, ld_dim = 1;
+ *                       SoA layout: ld_point = 1, ld_dim = n)
+ *   fr               : [n][3] doubles (nu_e, nu_mu, nu_tau)
+ *   status           : one byte per point, bit mask GF_ST_*
+ */
+#ifndef GOLEMFLAVOR_B200_H
+#define GOLEMFLAVOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GF_ABI_VERSION 1
+
+#define GF_MAX_DIM 16   /* parameters per point   */
+#define GF_MAX_BINS 64  /* energy bins per point  */
+
+/* return codes */
+#define GF_OK 0
+#define GF_ERR_ARG 1   /* bad argument (the reference raises ValueError/AssertionError) */
+#define GF_ERR_CUDA 2  /* CUDA runtime error / no device */
+
+/* per-point status bits (the reference raises or returns -inf mid-loop instead) */
+#define GF_ST_OUT_OF_PRIOR 1u /* lnprior = -inf        (llh.py:74-78)                  */
+#define GF_ST_NON_UNITARY 2u  /* unitarity residual > epsilon (fr.py:493-498 asserts)  */
+#define GF_ST_NON_FINITE 4u   /* NaN/Inf encountered (invalid angles, ...)             */
+#define GF_ST_ILL_COND 8u     /* eigen-gap below 1e-6: result limited by fp64 inputs   */
+#define GF_ST_REFINED 16u     /* informational: Jacobi refinement path was taken        */
+
+/* prior kinds == golemflavor/enums.py:38-41 (PriorsCateg) minus one */
+#define GF_PRIOR_UNIFORM 0
+#define GF_PRIOR_GAUSSIAN 1
+#define GF_PRIOR_LIMITEDGAUSS 2
+
+/* likelihood kinds */
+#define GF_LLH_FLAT 0     /* ln_prob = lnprior + llh_const  (scripts/mc_*.py: "return 1. # Flat LLH") */
+#define GF_LLH_GAUSSIAN 1 /* llh.multi_gaussian (llh.py:32-54)                                        */
+
+/* One sampled parameter: param.Param (param.py:24-91) flattened. */
+typedef struct gf_prior_dim {
+    double lo, hi;    /* Param.ranges                               */
+    double mu, sigma; /* Param.nominal_value, Param.std             */
+    int32_t kind;     /* GF_PRIOR_*                                 */
+    int32_t reserved;
+} gf_prior_dim;
+
+/*
+ * The closure `partial(ln_prob, args=..., asimov_paramset=..., llh_paramset=...)`
+ * (scripts/fr.py:182-187, examples/inference.ipynb cell 23) flattened:
+ * which theta column feeds which physical quantity, the fixed values of the
+ * quantities that are not sampled, the energy binning, the priors and the
+ * Gaussian likelihood constants.
+ */
+typedef struct gf_model {
+    int32_t ndim;         /* len(llh_paramset)                                            */
+    int32_t col_sm[4];    /* theta columns of s_12_2, c_13_4, s_23_2, dcp; -1 = fixed_sm  */
+    int32_t col_mass[2];  /* theta columns of m21_2, m3x_2;              -1 = fixed_mass  */
+    int32_t col_src[2];   /* theta columns of the SRCANGLES (sin^4 phi, cos 2psi);
+                             -1 = use fixed_src (args.source_ratio)                        */
+    int32_t col_np[4];    /* theta columns of the MMANGLES (NP mixing);   -1 = fixed_np   */
+    int32_t col_scale;    /* theta column of logLam (SCALE tag); -1 = fixed_loglam        */
+    int32_t col_x;        /* theta column of x, source = (x, 1-x, 0) (scripts/mc_x.py:187); -1 = unused */
+    int32_t no_bsm;       /* 1: skip the BSM path, fr = u_to_fr(source, sm_u) (notebook SM model) */
+    int32_t dimension;    /* args.dimension (3..8)                                         */
+    int32_t nbins;        /* len(args.binning) - 1                                         */
+    int32_t llh_kind;     /* GF_LLH_*                                                      */
+    int32_t emulate_underflow; /* 1: multi_gaussian returns -inf where the reference's pdf underflows */
+    int32_t reserved;
+    double fixed_sm[4];   /* default NUFIT angles (fr.py:313)                              */
+    double fixed_mass[2]; /* default MASS_EIGENVALUES (fr.py:42)                           */
+    double fixed_src[3];  /* args.source_ratio (need not be normalised)                    */
+    double fixed_np[4];   /* texture angles (fr.py:370-376)                                */
+    double fixed_loglam;
+    double bin_edges[GF_MAX_BINS + 1]; /* args.binning (GeV)                               */
+    double fr_bf[3];      /* injected / best-fit composition                               */
+    double smearing;      /* sigma of the Gaussian likelihood                              */
+    double offset;        /* multi_gaussian offset (-320)                                  */
+    double llh_const;     /* value of the flat likelihood (1.0 in scripts/mc_*.py)         */
+    double epsilon;       /* unitarity tolerance for GF_ST_NON_UNITARY (fr.py:319: 1e-7)   */
+    gf_prior_dim prior[GF_MAX_DIM];
+} gf_model;
+
+/* Monte-Carlo scan: scripts/mc_unitary.py, mc_x.py, mc_texture.py + plot.py:364-370 */
+#define GF_SCAN_UNITARY 0  /* 4 Haar-flat coords uniform -> U -> u_to_fr(source, U)  (mc_unitary.py:189-192) */
+#define GF_SCAN_X 1        /* as UNITARY with prior-drawn angles and source (x,1-x,0), x~U(0,1) (mc_x.py:186-192) */
+#define GF_SCAN_TEXTURE 2  /* SM params ~ priors, logLam ~ U(bounds), fixed texture, binned BSM path (mc_texture.py:216-221) */
+#define GF_SCAN_ANARCHIC 3 /* as TEXTURE with Haar-random NP mixing (Texture.NONE, 4 MMANGLES uniform) */
+
+typedef struct gf_scan_config {
+    int32_t mode;          /* GF_SCAN_*                                             */
+    int32_t nb;            /* nbins*oversample: histogram has (nb+1)^3 cells         */
+    uint64_t seed;         /* Philox4x32-10 key                                      */
+    uint64_t first_index;  /* global index of this shard's first sample              */
+    uint64_t count;        /* samples in this shard                                  */
+    int32_t sm_from_prior; /* 0: SM params fixed at model.fixed_*, 1: drawn from model.prior[0..5] */
+    int32_t reserved;
+} gf_scan_config;
+
+/* ---- library ---------------------------------------------------------- */
+int gf_abi_version(void);
+const char* gf_last_error(void);
+/* sm_count, compute capability and the SM clock (kHz) of the current device */
+int gf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int32_t* clock_khz);
+
+/* ---- fr.py ------------------------------------------------------------ */
+/* fr.angles_to_u(bsm_angles)                                   fr.py:116-162 */
+int gf_angles_to_u(const double* d_angles /*[n][4]*/, int64_t n, double* d_u /*[n][3][3][2]*/, void* stream);
+/* fr.angles_to_fr(src_angles)                                  fr.py:82-113  */
+int gf_angles_to_fr(const double* d_src_angles /*[n][2]*/, int64_t n, double* d_fr /*[n][3]*/, void* stream);
+/* fr.u_to_fr(source_fr, matrix)                                fr.py:502-536
+ * source_stride = 3 for one source per point, 0 for a single shared source. */
+int gf_u_to_fr(const double* d_source, int64_t source_stride, const double* d_u /*[n][3][3][2]*/, int64_t n,
+               double* d_fr /*[n][3]*/, void* stream);
+/* fr.cardano_eqn(ham)                                          fr.py:170-237
+ * Eigenvector matrices (columns = eigenvectors, ascending eigenvalue) and
+ * optionally the eigenvalues [n][3]; status gets GF_ST_NON_FINITE / ILL_COND. */
+int gf_eigvec_herm3(const double* d_ham /*[n][3][3][2]*/, int64_t n, double* d_vec /*[n][3][3][2]*/,
+                    double* d_eigval /*[n][3] or NULL*/, uint8_t* d_status /*[n] or NULL*/, void* stream);
+/* fr.params_to_BSMu(bsm_angles, dim, energy, mass_eigenvalues, sm_u, no_bsm, texture, check_uni, epsilon)
+ *                                                              fr.py:317-400
+ * bsm[n][5] = (np_s12_2, np_c13_4, np_s23_2, np_dcp, logLam) -- textures resolved by the caller
+ * (fr.py:370-376); mass_stride / smu_stride = 0 share one value across the batch. */
+int gf_params_to_bsmu(const double* d_bsm /*[n][5]*/, int32_t dim, const double* d_energy /*[n]*/,
+                      const double* d_mass, int64_t mass_stride /*2 or 0*/,
+                      const double* d_sm_u, int64_t smu_stride /*18 or 0*/, int32_t no_bsm, double epsilon,
+                      int64_t n, double* d_vec /*[n][3][3][2]*/, uint8_t* d_status /*[n] or NULL*/, void* stream);
+/* fr.flux_averaged_BSMu(theta, args, spectral_index, llh_paramset)  fr.py:403-458 */
+int gf_flux_averaged_fr(const gf_model* model, const double* d_theta, int64_t n, int64_t ld_point, int64_t ld_dim,
+                        double* d_fr /*[n][3]*/, uint8_t* d_status /*[n] or NULL*/, void* stream);
+
+/* ---- llh.py ----------------------------------------------------------- */
+/* llh.lnprior(theta, paramset)                                 llh.py:65-91  */
+int gf_lnprior(const gf_model* model, const double* d_theta, int64_t n, int64_t ld_point, int64_t ld_dim,
+               double* d_lnprior /*[n]*/, void* stream);
+/* llh.multi_gaussian(fr, fr_bf, smearing, offset)              llh.py:32-54  */
+int gf_multi_gaussian(const double* d_fr /*[n][3]*/, int64_t n, const double* h_fr_bf /*[3]*/, double smearing,
+                      double offset, int32_t emulate_underflow, double* d_llh /*[n]*/, void* stream);
+/* llh.ln_prob(theta, args, asimov_paramset, llh_paramset)      llh.py:121-130
+ * with the Gaussian flavor-ratio likelihood (examples/inference.ipynb cells 21-23).
+ * d_fr (optional) receives the measured composition of every in-prior point. */
+int gf_lnprob(const gf_model* model, const double* d_theta, int64_t n, int64_t ld_point, int64_t ld_dim,
+              double* d_lnprob /*[n]*/, double* d_fr /*[n][3] or NULL*/, uint8_t* d_status /*[n] or NULL*/,
+              void* stream);
+/* Same call on HOST buffers (row-major theta[n][ndim]): chunked H2D -> kernel -> D2H
+ * pipeline on internal streams; returns after the results are in h_lnprob. */
+int gf_lnprob_host(const gf_model* model, const double* h_theta, int64_t n, double* h_lnprob,
+                   double* h_fr /*or NULL*/, uint8_t* h_status /*or NULL*/);
+
+/* ---- Monte-Carlo scans ------------------------------------------------ */
+/* Draw `count` samples with Philox4x32-10 (counter = global sample index), push them through the
+ * flavor path selected by cfg->mode and accumulate the ternary histogram
+ * np.histogramdd(frs, bins=(nb+1,)*3, range=((0,1),)*3) (plot.py:364-370) into d_hist (ADDS to it).
+ * d_accepted (optional, 1 counter) ADDS the number of samples inside the prior box. */
+int gf_scan_hist(const gf_model* model, const gf_scan_config* cfg, unsigned long long* d_hist /*[(nb+1)^3]*/,
+                 unsigned long long* d_accepted /*[1] or NULL*/, void* stream);
+/* Same sampler, but writes the drawn theta [count][ndim_scan] and fr [count][3] (parity/debug). */
+int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_theta /*[count][8] or NULL*/,
+                    double* d_fr /*[count][3]*/, uint8_t* d_status /*or NULL*/, void* stream);
+/* Histogram of given compositions (bit-exact np.histogramdd), ADDS into d_hist. */
+int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsigned long long* d_hist, void* stream);
+
+/* ---- measurement helper ----------------------------------------------- */
+/* DFMA microbenchmark: runs `iters` dependent-chain FMAs x `chains` per thread on a full grid and
+ * returns the number of fp64 FLOPs issued (2 per FMA) in *flops; time it with CUDA events on `stream`. */
+int gf_fp64_peak_probe(int64_t iters, double* d_sink /*[>= 1]*/, double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLEMFLAVOR_B200_H */
