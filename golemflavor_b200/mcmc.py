@@ -1,0 +1,207 @@
+"""emcee driver for the flavor-ratio analysis (drop-in for ``golemflavor/mcmc.py``).
+
+The reference hands ``ln_prob`` to ``emcee.EnsembleSampler(nwalkers, ndim, ln_prob, threads=N)``
+(``mcmc.py:29-31``), which scores one walker per Python call in a multiprocessing pool.  emcee is an
+un-vendored, unpinned dependency of the reference and is not needed here: ``EnsembleSampler`` below
+implements the same affine-invariant stretch move (Goodman & Weare 2010; red/blue half-ensembles,
+a = 2) with the emcee-2 attributes the reference driver touches, and calls the log-posterior
+*vectorised* -- each half-ensemble is ONE call ``ln_prob(theta[nwalkers/2, ndim]) -> [nwalkers/2]``,
+i.e. one CUDA kernel launch.  Only the proposal bookkeeping (a few vector operations on
+``nwalkers x ndim`` numbers) runs in NumPy; every log-posterior value comes from the GPU.
+"""
+
+import os
+import sys
+
+import numpy as np
+
+__all__ = ['EnsembleSampler', 'mcmc', 'flat_seed', 'gaussian_seed', 'save_chains', 'integrated_time']
+
+
+def _progress(iterable, total):
+    if os.environ.get('GOLEMFLAVOR_PROGRESS', '0') != '1':
+        return iterable
+    try:
+        from tqdm import tqdm
+    except ImportError:
+        return iterable
+    return tqdm(iterable, total=total)
+
+
+def integrated_time(x, c=5.0):
+    """Integrated autocorrelation time per dimension of a chain ``x[nsteps, nwalkers, ndim]``
+    (FFT autocorrelation averaged over walkers, Sokal's automatic window M >= c tau)."""
+    x = np.asarray(x, dtype=np.float64)
+    nsteps, nwalkers, ndim = x.shape
+    n = 1 << int(np.ceil(np.log2(max(2 * nsteps, 2))))
+    tau = np.empty(ndim)
+    for d in range(ndim):
+        acf = np.zeros(nsteps)
+        for w in range(nwalkers):
+            y = x[:, w, d] - x[:, w, d].mean()
+            f = np.fft.rfft(y, n=n)
+            a = np.fft.irfft(f * np.conjugate(f), n=n)[:nsteps]
+            acf += a / a[0] if a[0] > 0 else 0.0
+        acf /= nwalkers
+        taus = 2.0 * np.cumsum(acf) - 1.0
+        window = np.arange(nsteps) >= c * taus
+        m = int(np.argmax(window)) if window.any() else nsteps - 1
+        tau[d] = taus[m]
+    return tau
+
+
+class EnsembleSampler(object):
+    """Affine-invariant ensemble sampler with the emcee-2 surface used by the reference
+    (``mcmc.py:29-49``): ``sample(p0, iterations=)``, ``reset()``, ``chain``, ``lnprobability``,
+    ``acceptance_fraction``, ``acor``, ``flatchain``, ``run_mcmc``.
+
+    ``lnpostfn`` must accept ``theta[n, ndim]`` and return ``[n]`` (``vectorize=True``, the
+    default here); with ``vectorize=False`` it is mapped over walkers like emcee-2 does.
+    ``threads`` is accepted and ignored: the parallelism is inside the kernel."""
+
+    def __init__(self, nwalkers, ndim, lnpostfn, a=2.0, args=(), kwargs=None, threads=1, vectorize=True, seed=None):
+        if nwalkers % 2 != 0:
+            raise ValueError('The number of walkers must be even.')
+        if nwalkers < 2 * ndim:
+            raise ValueError('The number of walkers needs to be more than twice the dimension of your parameter space.')
+        self.k, self.dim, self.a = int(nwalkers), int(ndim), float(a)
+        self.lnpostfn, self.args, self.kwargs = lnpostfn, tuple(args), dict(kwargs or {})
+        self.vectorize = bool(vectorize)
+        self.threads = threads
+        self._random = np.random.RandomState(seed)
+        self.ncalls = 0  # number of log-posterior (kernel) calls
+        self.reset()
+
+    # -- bookkeeping ---------------------------------------------------------------------------
+    def reset(self):
+        self._chain = np.empty((self.k, 0, self.dim))
+        self._lnprob = np.empty((self.k, 0))
+        self.naccepted = np.zeros(self.k)
+        self.iterations = 0
+        self._last_run_mcmc_result = None
+
+    chain = property(lambda self: self._chain)
+    lnprobability = property(lambda self: self._lnprob)
+    flatchain = property(lambda self: self._chain.reshape((-1, self.dim)))
+    random_state = property(lambda self: self._random.get_state())
+
+    @property
+    def acceptance_fraction(self):
+        return self.naccepted / max(self.iterations, 1)
+
+    @property
+    def acor(self):
+        return self.get_autocorr_time()
+
+    def get_autocorr_time(self, c=5.0):
+        if self._chain.shape[1] < 50:
+            raise RuntimeError('The chain is too short to reliably estimate the autocorrelation time')
+        return integrated_time(np.swapaxes(self._chain, 0, 1), c=c)
+
+    def _lnprob_of(self, p):
+        self.ncalls += 1
+        if self.vectorize:
+            lp = self.lnpostfn(p, *self.args, **self.kwargs)
+            lp = lp.detach().cpu().numpy() if hasattr(lp, 'detach') else np.asarray(lp, dtype=np.float64)
+        else:
+            lp = np.array([self.lnpostfn(row, *self.args, **self.kwargs) for row in p], dtype=np.float64)
+        lp = lp.reshape(-1)
+        if lp.shape[0] != p.shape[0]:
+            raise ValueError('lnpostfn returned {0} values for {1} walkers'.format(lp.shape[0], p.shape[0]))
+        if np.any(np.isnan(lp)):
+            raise ValueError('lnprob returned NaN.')  # emcee raises on NaN log-probabilities
+        return lp
+
+    # -- sampling ------------------------------------------------------------------------------
+    def sample(self, p0, lnprob0=None, rstate0=None, iterations=1, thin=1, storechain=True):
+        """Advance the ensemble; yields ``(pos, lnprob, rstate)`` after every step."""
+        if rstate0 is not None:
+            self._random.set_state(rstate0)
+        p = np.array(p0, dtype=np.float64)
+        if p.shape != (self.k, self.dim):
+            raise ValueError('p0 must have shape (nwalkers, ndim) = {0}, got {1}'.format((self.k, self.dim), p.shape))
+        lnprob = self._lnprob_of(p) if lnprob0 is None else np.array(lnprob0, dtype=np.float64)
+        n_store = iterations // thin if storechain else 0
+        base = self._chain.shape[1]
+        if storechain:
+            self._chain = np.concatenate((self._chain, np.zeros((self.k, n_store, self.dim))), axis=1)
+            self._lnprob = np.concatenate((self._lnprob, np.zeros((self.k, n_store))), axis=1)
+        half = self.k // 2
+        first, second = slice(0, half), slice(half, self.k)
+        for i in range(int(iterations)):
+            self.iterations += 1
+            for S0, S1 in ((first, second), (second, first)):
+                s, c = p[S0], p[S1]
+                ns, nc = s.shape[0], c.shape[0]
+                zz = ((self.a - 1.0) * self._random.rand(ns) + 1.0) ** 2 / self.a
+                partner = c[self._random.randint(nc, size=ns)]
+                q = partner - zz[:, None] * (partner - s)
+                newlnprob = self._lnprob_of(q)
+                with np.errstate(invalid='ignore'):
+                    lnpdiff = (self.dim - 1.0) * np.log(zz) + newlnprob - lnprob[S0]
+                accept = lnpdiff > np.log(self._random.rand(ns))
+                idx = np.arange(S0.start, S0.stop)[accept]
+                p[idx] = q[accept]
+                lnprob[idx] = newlnprob[accept]
+                self.naccepted[idx] += 1
+            if storechain and (i + 1) % thin == 0 and (i + 1) // thin <= n_store:
+                ind = base + (i + 1) // thin - 1
+                self._chain[:, ind, :] = p
+                self._lnprob[:, ind] = lnprob
+            yield p, lnprob, self.random_state
+
+    def run_mcmc(self, pos0, N, rstate0=None, lnprob0=None, **kwargs):
+        if pos0 is None:
+            if self._last_run_mcmc_result is None:
+                raise ValueError('Cannot have pos0=None if run_mcmc has never been called.')
+            pos0, lnprob0, rstate0 = self._last_run_mcmc_result
+        results = None
+        for results in self.sample(pos0, lnprob0, rstate0, iterations=N, **kwargs):
+            pass
+        self._last_run_mcmc_result = results
+        return results
+
+
+def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=True, seed=None):
+    """Run burn-in, reset, run, flatten walker-major (``mcmc.py:27-53``).  Returns ``samples[nwalkers*nsteps, ndim]``."""
+    sampler = EnsembleSampler(nwalkers, ndim, ln_prob, threads=threads, vectorize=vectorize, seed=seed)
+    print("Running burn-in")
+    pos = np.asarray(p0)
+    for pos, _, _ in _progress(sampler.sample(p0, iterations=burnin), burnin):
+        pass
+    sampler.reset()
+    print("Finished burn-in")
+    print("Running")
+    for _ in _progress(sampler.sample(pos, iterations=nsteps), nsteps):
+        pass
+    print("Finished")
+    samples = sampler.chain.reshape((-1, ndim))
+    print('acceptance fraction', sampler.acceptance_fraction)
+    print('sum of acceptance fraction', np.sum(sampler.acceptance_fraction))
+    print('np.unique(samples[:,0]).shape', np.unique(samples[:, 0]).shape)
+    try:
+        print('autocorrelation', sampler.acor)
+    except Exception:
+        print('WARNING : NEED TO RUN MORE SAMPLES')
+    mcmc.last_sampler = sampler
+    return samples
+
+
+def flat_seed(paramset, nwalkers):
+    """Uniform starting positions inside the ``Param.seed`` boxes (``mcmc.py:88-96``)."""
+    seeds = np.array(paramset.seeds, dtype=np.float64)
+    return np.random.uniform(low=seeds[:, 0], high=seeds[:, 1], size=[nwalkers, len(paramset)])
+
+
+def gaussian_seed(paramset, nwalkers):
+    """Gaussian starting positions around the current values (``mcmc.py:99-105``)."""
+    return np.random.normal(paramset.values, paramset.stds, size=[nwalkers, len(paramset)])
+
+
+def save_chains(chains, outfile):
+    """``np.save`` of the chains; like the reference (``mcmc.py:108-126``) ``.npy`` is always appended."""
+    directory = os.path.dirname(outfile)
+    if directory and not os.path.isdir(directory):
+        os.makedirs(directory, exist_ok=True)
+    print('Saving chains to location {0}'.format(outfile + '.npy'))
+    np.save(outfile + '.npy', chains)

@@ -1,0 +1,158 @@
+"""Monte-Carlo prior scans -> ternary flavor histograms (``scripts/mc_unitary.py``, ``mc_x.py``,
+``mc_texture.py`` + the histogram definition of ``plot.flavor_contour``, ``plot.py:364-370``).
+
+The reference obtains prior samples by running emcee on a flat likelihood (``mc_unitary.py:121-131``),
+maps ``angles_to_u`` / ``u_to_fr`` / ``flux_averaged_BSMu`` over the chain in Python
+(``mc_unitary.py:189-192``, ``mc_x.py:186-192``, ``mc_texture.py:216-221``) and histograms at plot time.
+Here a scan is ONE fused kernel per GPU: Philox4x32-10 draws (counter = global sample index) ->
+flavor physics -> block-private shared-memory histogram.  Across GPUs the global index range is
+split into contiguous shards -- the result is bit-identical for any number of ranks -- and the
+per-rank histograms are summed by a single NCCL all-reduce.
+"""
+
+import ctypes as C
+from argparse import Namespace
+
+import numpy as np
+
+from . import _lib
+from . import model as _model
+from .enums import ParamTag, PriorsCateg, Texture, enum_name
+from .param import Param, ParamSet
+
+__all__ = ['sm_paramset', 'scan_paramset', 'scan_model', 'scan_histogram', 'scan_samples', 'ternary_histogram',
+           'shard_range']
+
+DEFAULT_BINNING = np.logspace(np.log10(6e4), np.log10(1e7), 21)  # fr.py:283-285
+
+
+def sm_paramset(with_mass=True, gaussian=True):
+    """The SM nuisance parameters of ``scripts/mc_texture.py:34-56`` / ``scripts/fr.py:38-49``:
+    three mixing angles with LIMITEDGAUSS priors, a flat CP phase and (optionally) the two mass
+    splittings with GAUSSIAN priors."""
+    lg = PriorsCateg.LIMITEDGAUSS if gaussian else None
+    g = PriorsCateg.GAUSSIAN if gaussian else None
+    e = 1e-9
+    tag = ParamTag.SM_ANGLES
+    ps = [
+        Param(name='s_12_2', value=0.307, seed=[0.26, 0.35], ranges=[0., 1.], std=0.013, prior=lg, tag=tag),
+        Param(name='c_13_4', value=(1 - 0.02206) ** 2, seed=[0.950, 0.961], ranges=[0., 1.], std=0.00147, prior=lg, tag=tag),
+        Param(name='s_23_2', value=0.538, seed=[0.31, 0.75], ranges=[0., 1.], std=0.069, prior=lg, tag=tag),
+        Param(name='dcp', value=4.08404, seed=[0 + e, 2 * np.pi - e], ranges=[0., 2 * np.pi], std=2.0, tag=tag),
+    ]
+    if with_mass:
+        ps += [
+            Param(name='m21_2', value=7.40E-23, seed=[7.2E-23, 7.6E-23], ranges=[6.80E-23, 8.02E-23], std=2.1E-24, prior=g, tag=tag),
+            Param(name='m3x_2', value=2.494E-21, seed=[2.46E-21, 2.53E-21], ranges=[2.399E-21, 2.593E-21], std=3.3E-23, prior=g, tag=tag),
+        ]
+    return ps
+
+
+def scan_paramset(mode, dimension=6):
+    """ParamSet of a scan mode.
+
+    unitary  : 4 Haar-flat coordinates, uniform                      (mc_unitary.py:34-46)
+    x        : 3 angles with LIMITEDGAUSS priors + dcp + x ~ U(0,1)  (mc_x.py:34-49)
+    texture  : 6 SM params with priors + logLam ~ U(SCALE_BOUNDARIES) (mc_texture.py:34-67)
+    anarchic : texture + 4 Haar-flat new-physics mixing coordinates   (Texture.NONE)
+    """
+    mode = mode.lower()
+    if mode == 'unitary':
+        return ParamSet(sm_paramset(with_mass=False, gaussian=False))
+    if mode == 'x':
+        return ParamSet(sm_paramset(with_mass=False) + [Param(name='astroX', value=0.5, seed=[0., 1.], ranges=[0., 1.], std=0.1, tag=ParamTag.SRCANGLES)])
+    if mode in ('texture', 'anarchic'):
+        ps = sm_paramset(with_mass=True)
+        if mode == 'anarchic':
+            tag = ParamTag.MMANGLES
+            ps += [Param(name='np_s_12_2', value=0.5, ranges=[0., 1.], std=0.2, tag=tag),
+                   Param(name='np_c_13_4', value=0.5, ranges=[0., 1.], std=0.2, tag=tag),
+                   Param(name='np_s_23_2', value=0.5, ranges=[0., 1.], std=0.2, tag=tag),
+                   Param(name='np_dcp', value=np.pi, ranges=[0., 2 * np.pi], std=0.2, tag=tag)]
+        b = _model.SCALE_BOUNDARIES[int(dimension)]
+        ps.append(Param(name='logLam', value=float(np.mean(b)), ranges=list(b), std=3, tag=ParamTag.SCALE))
+        return ParamSet(ps)
+    raise ValueError("scan mode must be 'unitary', 'x', 'texture' or 'anarchic', got {0!r}".format(mode))
+
+
+def scan_model(mode, source_ratio=(1, 2, 0), dimension=6, texture=Texture.OET, binning=DEFAULT_BINNING, paramset=None):
+    """Flat model of a scan (flat likelihood, as ``mc_*.py`` ``triangle_llh``: "return 1. # Flat LLH")."""
+    mode = mode.lower()
+    pset = paramset if paramset is not None else scan_paramset(mode, dimension)
+    if mode == 'anarchic':
+        texture = Texture.NONE
+    args = Namespace(source_ratio=_np_norm(source_ratio), dimension=int(dimension), texture=texture,
+                     binning=np.asarray(binning, dtype=np.float64), no_bsm=mode in ('unitary', 'x'))
+    return _model.flatten(args, None, pset, likelihood='FLAT')
+
+
+def _np_norm(x):
+    x = np.asarray(x, dtype=np.float64)
+    return x / x.sum()
+
+
+def shard_range(count, rank, world_size, first_index=0):
+    """Contiguous shard [first, first + n) of the global sample index range for ``rank``."""
+    base, rem = divmod(int(count), int(world_size))
+    n = base + (1 if rank < rem else 0)
+    start = first_index + rank * base + min(rank, rem)
+    return start, n
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def scan_histogram(fm, count, nb=25, seed=26, first_index=0, distributed=True, out=None, return_tensor=False):
+    """Histogram of ``count`` prior samples: ``np.histogramdd(frs, bins=(nb+1,)*3, range=((0,1),)*3)``.
+
+    With an initialised ``torch.distributed`` process group (and ``distributed=True``) the index range
+    is sharded over the ranks and the counts are summed with one all-reduce; every rank returns the
+    full histogram.  ``seed`` defaults to the reference scripts' ``--seed 26`` (``mc_unitary.py:97``)."""
+    torch = _lib.torch_cuda()
+    dist = _dist() if distributed else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    start, n = shard_range(count, rank, world, first_index)
+    cells = (nb + 1) ** 3
+    hist = out if out is not None else torch.zeros((cells,), dtype=torch.int64, device='cuda')
+    kept = torch.zeros((1,), dtype=torch.int64, device='cuda')
+    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=int(nb))
+    _lib.check(_lib.load().gf_scan_hist(fm.ref, C.byref(cfg), _lib.ptr(hist), _lib.ptr(kept), _lib.stream_ptr(torch)))
+    if dist and world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kept, op=dist.ReduceOp.SUM)
+    h = hist.reshape(nb + 1, nb + 1, nb + 1)
+    if return_tensor:
+        return h, kept
+    return h.cpu().numpy(), int(kept.item())
+
+
+def scan_samples(fm, count, seed=26, first_index=0, return_tensor=False):
+    """The drawn parameters ``theta[count, ndim]``, compositions ``fr[count, 3]`` and status bytes
+    of a scan (what the reference saves with ``np.save``, ``mc_unitary.py:193``)."""
+    torch = _lib.torch_cuda()
+    theta = torch.empty((count, fm.ndim), dtype=torch.float64, device='cuda')
+    fr = torch.empty((count, 3), dtype=torch.float64, device='cuda')
+    st = torch.empty((count,), dtype=torch.uint8, device='cuda')
+    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(first_index), count=int(count), nb=0)
+    _lib.check(_lib.load().gf_scan_samples(fm.ref, C.byref(cfg), _lib.ptr(theta), _lib.ptr(fr), _lib.ptr(st),
+                                           _lib.stream_ptr(torch)))
+    if return_tensor:
+        return theta, fr, st
+    return theta.cpu().numpy(), fr.cpu().numpy(), st.cpu().numpy()
+
+
+def ternary_histogram(frs, nb=25, return_tensor=False):
+    """``np.histogramdd(frs, bins=(nb+1,)*3, range=((0,1),)*3)`` (``plot.py:364-370``), bit-exact."""
+    torch = _lib.torch_cuda()
+    f = _lib.to_device(frs, torch, 3).reshape(-1, 3)
+    hist = torch.zeros(((nb + 1) ** 3,), dtype=torch.int64, device='cuda')
+    _lib.check(_lib.load().gf_ternary_hist(_lib.ptr(f), f.shape[0], int(nb), _lib.ptr(hist), _lib.stream_ptr(torch)))
+    h = hist.reshape(nb + 1, nb + 1, nb + 1)
+    return h if return_tensor else h.cpu().numpy()

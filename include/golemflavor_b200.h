@@ -100,27 +100,42 @@ typedef struct gf_model {
     gf_prior_dim prior[GF_MAX_DIM];
 } gf_model;
 
-/* Monte-Carlo scan: scripts/mc_unitary.py, mc_x.py, mc_texture.py + plot.py:364-370 */
-#define GF_SCAN_UNITARY 0  /* 4 Haar-flat coords uniform -> U -> u_to_fr(source, U)  (mc_unitary.py:189-192) */
-#define GF_SCAN_X 1        /* as UNITARY with prior-drawn angles and source (x,1-x,0), x~U(0,1) (mc_x.py:186-192) */
-#define GF_SCAN_TEXTURE 2  /* SM params ~ priors, logLam ~ U(bounds), fixed texture, binned BSM path (mc_texture.py:216-221) */
-#define GF_SCAN_ANARCHIC 3 /* as TEXTURE with Haar-random NP mixing (Texture.NONE, 4 MMANGLES uniform) */
-
+/*
+ * Monte-Carlo scan: scripts/mc_unitary.py, mc_x.py, mc_texture.py + plot.py:364-370.
+ * The reference draws prior samples by running emcee on a flat likelihood; here sample i draws
+ * parameter k of the model directly from its prior (model.prior[k]: uniform in `ranges`, or a
+ * Gaussian truncated to `ranges`, by inverse CDF) using Philox4x32-10 with
+ *   key = (lo32(seed), hi32(seed)),  counter = (lo32(i), hi32(i), k / 4, 0),  word k % 4,
+ *   uniform = (word + 0.5) * 2^-32,
+ * so that the result is independent of the launch geometry and of the number of GPUs.
+ * Which scan it is (unitary / x / texture / anarchic) is entirely a property of the model:
+ *   unitary  : 4 SM_ANGLES columns, no_bsm = 1, fixed source          (mc_unitary.py:189-192)
+ *   x        : unitary + col_x, source = (x, 1-x, 0)                  (mc_x.py:186-192)
+ *   texture  : 6 SM columns + logLam, fixed texture angles, 20 bins   (mc_texture.py:216-221)
+ *   anarchic : texture + 4 MMANGLES columns (Haar-random NP mixing)   (Texture.NONE)
+ */
 typedef struct gf_scan_config {
-    int32_t mode;          /* GF_SCAN_*                                             */
-    int32_t nb;            /* nbins*oversample: histogram has (nb+1)^3 cells         */
-    uint64_t seed;         /* Philox4x32-10 key                                      */
-    uint64_t first_index;  /* global index of this shard's first sample              */
-    uint64_t count;        /* samples in this shard                                  */
-    int32_t sm_from_prior; /* 0: SM params fixed at model.fixed_*, 1: drawn from model.prior[0..5] */
+    uint64_t seed;        /* Philox4x32-10 key                                      */
+    uint64_t first_index; /* global index of this shard's first sample              */
+    uint64_t count;       /* samples in this shard                                  */
+    int32_t nb;           /* nbins*oversample: histogram has (nb+1)^3 cells         */
     int32_t reserved;
 } gf_scan_config;
 
 /* ---- library ---------------------------------------------------------- */
 int gf_abi_version(void);
+/* sizeof(gf_model) / sizeof(gf_scan_config) / sizeof(gf_prior_dim) for which = 0 / 1 / 2: lets a
+ * foreign-language binding verify its struct layout at load time. */
+uint64_t gf_sizeof(int32_t which);
 const char* gf_last_error(void);
 /* sm_count, compute capability and the SM clock (kHz) of the current device */
 int gf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int32_t* clock_khz);
+/* Page-locked host buffers for the *_host calls (pageable buffers work too, through an internal
+ * pinned staging ring, at memcpy speed). */
+int gf_host_alloc(void** h_ptr, uint64_t bytes);
+int gf_host_free(void* h_ptr);
+/* Validate a model without launching anything (same checks as every compute call). */
+int gf_model_check(const gf_model* model);
 
 /* ---- fr.py ------------------------------------------------------------ */
 /* fr.angles_to_u(bsm_angles)                                   fr.py:116-162 */
@@ -173,9 +188,9 @@ int gf_lnprob_host(const gf_model* model, const double* h_theta, int64_t n, doub
  * d_accepted (optional, 1 counter) ADDS the number of samples inside the prior box. */
 int gf_scan_hist(const gf_model* model, const gf_scan_config* cfg, unsigned long long* d_hist /*[(nb+1)^3]*/,
                  unsigned long long* d_accepted /*[1] or NULL*/, void* stream);
-/* Same sampler, but writes the drawn theta [count][ndim_scan] and fr [count][3] (parity/debug). */
-int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_theta /*[count][8] or NULL*/,
-                    double* d_fr /*[count][3]*/, uint8_t* d_status /*or NULL*/, void* stream);
+/* Same sampler, but writes the drawn theta [count][ndim] and fr [count][3] (parity/debug; cfg->nb unused). */
+int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_theta /*[count][ndim] or NULL*/,
+                    double* d_fr /*[count][3] or NULL*/, uint8_t* d_status /*[count] or NULL*/, void* stream);
 /* Histogram of given compositions (bit-exact np.histogramdd), ADDS into d_hist. */
 int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsigned long long* d_hist, void* stream);
 
@@ -183,6 +198,8 @@ int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsign
 /* DFMA microbenchmark: runs `iters` dependent-chain FMAs x `chains` per thread on a full grid and
  * returns the number of fp64 FLOPs issued (2 per FMA) in *flops; time it with CUDA events on `stream`. */
 int gf_fp64_peak_probe(int64_t iters, double* d_sink /*[>= 1]*/, double* flops, void* stream);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+uint64_t gf_launch_count(void);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,89 @@
+"""Host instantiation of the kernels' per-point functions -- TEST INFRASTRUCTURE ONLY
+(see harness.cu).  Built on demand with nvcc; links against the product library for the model
+flattening (``gf_build_dev_model``)."""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from golemflavor_b200 import _lib, build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, 'libgf_host_harness.so')
+SRC = os.path.join(HERE, 'harness.cu')
+_h = None
+
+
+def load():
+    global _h
+    if _h is not None:
+        return _h
+    lib_path = build.build_library()
+    deps = [SRC, lib_path] + [os.path.join(build.CSRC, f) for f in build.HEADERS]
+    if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
+        cuda_inc = os.path.join(os.path.dirname(os.path.dirname(build.nvcc_path())), 'include')
+        cmd = ['g++', '-x', 'c++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared', '-I' + cuda_inc,
+               '-o', SO, SRC, '-L' + build.LIB_DIR, '-lgolemflavor_b200', '-Wl,-rpath,' + build.LIB_DIR]
+        subprocess.run(cmd, check=True)
+    _lib.load()
+    _h = C.CDLL(SO)
+    return _h
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def lnprob(fm, theta):
+    th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
+    n = th.shape[0]
+    lnp, fr, st = np.empty(n), np.empty((n, 3)), np.empty(n, dtype=np.uint8)
+    rc = load().hh_lnprob(fm.ref, _p(th), C.c_int64(n), _p(lnp), _p(fr), _p(st))
+    _lib.check(rc)
+    return lnp, fr, st
+
+
+def fr(fm, theta):
+    th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
+    n = th.shape[0]
+    out, st = np.empty((n, 3)), np.empty(n, dtype=np.uint8)
+    _lib.check(load().hh_fr(fm.ref, _p(th), C.c_int64(n), _p(out), _p(st)))
+    return out, st
+
+
+def lnprior(fm, theta):
+    th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
+    out = np.empty(th.shape[0])
+    _lib.check(load().hh_lnprior(fm.ref, _p(th), C.c_int64(th.shape[0]), _p(out)))
+    return out
+
+
+def philox(ctr, key):
+    ctr = np.ascontiguousarray(ctr, dtype=np.uint32).reshape(-1, 4)
+    out = np.empty_like(ctr)
+    load().hh_philox(_p(ctr), C.c_int64(ctr.shape[0]), C.c_uint32(key[0]), C.c_uint32(key[1]), _p(out))
+    return out
+
+
+def draw(fm, seed, first, n):
+    theta = np.empty((n, fm.ndim))
+    _lib.check(load().hh_draw(fm.ref, C.c_uint64(seed), C.c_uint64(first), C.c_int64(n), _p(theta)))
+    return theta
+
+
+def hist(frs, nb):
+    f = np.ascontiguousarray(frs, dtype=np.float64).reshape(-1, 3)
+    h = np.zeros((nb + 1) ** 3, dtype=np.uint64)
+    load().hh_hist(_p(f), C.c_int64(f.shape[0]), C.c_int(nb), _p(h))
+    return h.reshape(nb + 1, nb + 1, nb + 1).astype(np.int64)
+
+
+def eig(ham):
+    h = np.ascontiguousarray(np.asarray(ham, dtype=np.complex128)).reshape(-1, 3, 3)
+    n = h.shape[0]
+    hv = h.view(np.float64).reshape(n, 18)
+    lam, vec, xf, ok = np.empty((n, 3)), np.empty((n, 18)), np.empty((n, 9)), np.empty(n, dtype=np.uint8)
+    load().hh_eig(_p(hv), C.c_int64(n), _p(lam), _p(vec), _p(xf), _p(ok))
+    return lam, vec.view(np.complex128).reshape(n, 3, 3), xf.reshape(n, 3, 3), ok.astype(bool)

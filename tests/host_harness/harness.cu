@@ -1,0 +1,84 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked into libgolemflavor_b200.so, never imported by the
+ * product package.
+ *
+ * The per-point functions of golemflavor_b200/csrc/gf_*.cuh are `__host__ __device__` (the library
+ * uses the host instantiation for model constants such as the texture matrix).  This harness
+ * instantiates them on the host in a plain loop so that the CPU test-suite (`-m "not gpu"`, no GPU
+ * in the build container) can compare the kernels' ALGORITHM -- closed-form eigen stage, Jacobi
+ * fallback thresholds, prior / likelihood composition, Philox stream, histogram bin index -- with
+ * the oracle before any GPU time is spent.  The GPU parity tests (`-m gpu`) remain the parity
+ * tests proper and go through the C ABI.
+ */
+#include <string.h>
+
+#include "../../golemflavor_b200/csrc/gf_common.cuh"
+#include "../../golemflavor_b200/csrc/gf_scan_dev.cuh"
+
+extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        auto get = [&](int k) { return theta[i * d.ndim + k]; };
+        unsigned s = 0u;
+        double f[3];
+        lnp[i] = gf_point_lnprob(d, get, f, s);
+        if (fr) memcpy(fr + 3 * i, f, sizeof(f));
+        if (st) st[i] = (uint8_t)s;
+    }
+    return 0;
+}
+
+extern "C" int hh_fr(const gf_model* model, const double* theta, int64_t n, double* fr, uint8_t* st) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        auto get = [&](int k) { return theta[i * d.ndim + k]; };
+        gf_point q;
+        gf_resolve_point(d, get, q);
+        const unsigned s = gf_point_fr(d, q, fr + 3 * i);
+        if (st) st[i] = (uint8_t)s;
+    }
+    return 0;
+}
+
+extern "C" int hh_lnprior(const gf_model* model, const double* theta, int64_t n, double* lnp) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    for (int64_t i = 0; i < n; ++i) lnp[i] = gf_point_lnprior(d, [&](int k) { return theta[i * d.ndim + k]; });
+    return 0;
+}
+
+extern "C" void hh_philox(const uint32_t* ctr /*[n][4]*/, int64_t n, uint32_t k0, uint32_t k1, uint32_t* out /*[n][4]*/) {
+    for (int64_t i = 0; i < n; ++i) {
+        const gf_u4 r = gf_philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], k0, k1);
+        out[4 * i] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+    }
+}
+
+extern "C" int hh_draw(const gf_model* model, uint64_t seed, uint64_t first, int64_t n, double* theta) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    for (int64_t i = 0; i < n; ++i) gf_draw_theta(d, seed, first + (uint64_t)i, theta + i * d.ndim);
+    return 0;
+}
+
+extern "C" void hh_hist(const double* fr, int64_t n, int nb, unsigned long long* hist) {
+    const int nb1 = nb + 1;
+    const double step = 1.0 / (double)nb1;
+    for (int64_t i = 0; i < n; ++i) {
+        const int c = gf_cell_index(fr + 3 * i, nb1, step);
+        if (c >= 0) ++hist[c];
+    }
+}
+
+extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, double* vec, double* x_fast, uint8_t* fast_ok) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double* h = ham + 18 * i;
+        gfp_herm3 m;
+        m.d0 = h[0]; m.d1 = h[8]; m.d2 = h[16];
+        m.ar = h[2]; m.ai = h[3]; m.br = h[4]; m.bi = h[5]; m.cr = h[10]; m.ci = h[11];
+        gfp_herm3_eig_sorted(m, lam + 3 * i, vec + 18 * i);
+        fast_ok[i] = gfp_herm3_abs2_fast(m, x_fast + 9 * i) ? 1 : 0;
+    }
+}

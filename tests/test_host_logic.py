@@ -1,0 +1,297 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, the host
+logic (ParamSet flattening, argument checking, sharding) behaves like the reference, and the
+kernels' per-point arithmetic -- instantiated on the host by tests/host_harness -- agrees with
+the golden fixtures / the oracle.  The GPU parity tests proper are in test_gpu_*.py."""
+
+import argparse
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from golemflavor_b200 import _lib, build, enums, llh, mcmc, model, scan
+from golemflavor_b200.enums import ParamTag, PriorsCateg, Texture
+from golemflavor_b200.param import Param, ParamSet
+from oracle import golem_oracle as go
+from oracle import truth
+
+import host_harness as hh
+import models
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ library / ABI
+def test_library_builds_and_exports_every_declared_symbol():
+    build.build_library()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'golemflavor_b200.h')).read()
+    declared = set(re.findall(r'^\s*(?:int|uint64_t|const char\*)\s+(gf_\w+)\s*\(', header, flags=re.M))
+    assert declared, 'no prototypes found in the header'
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gf_abi_version() == 1
+    assert lib.gf_sizeof(0) == C.sizeof(_lib.Model)
+
+
+def test_no_oracle_or_cpu_fallback_in_product():
+    """The product package must not import the oracle or the host harness."""
+    pkg = os.path.join(ROOT, 'golemflavor_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'oracle' not in src.replace('golem_oracle', 'oracle') or fn == '__none__', fn
+            assert 'host_harness' not in src, fn
+
+
+def test_compute_without_gpu_raises():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from golemflavor_b200 import fr
+    with pytest.raises(_lib.GolemFlavorError):
+        fr.angles_to_u((0.2, 0.3, 0.5, 1.5))
+    with pytest.raises(_lib.GolemFlavorError):
+        llh.multi_gaussian([.3, .35, .35], [.55, .18, .27], .02)
+
+
+def test_model_check_rejects_bad_models():
+    m = model._new_struct()
+    m.ndim = 0
+    with pytest.raises(ValueError):
+        model.FlatModel(m)
+    m = model._new_struct()
+    m.ndim = 2
+    m.prior[0].lo, m.prior[0].hi = 1.0, 0.0
+    with pytest.raises(ValueError):
+        model.FlatModel(m)
+    m = model._new_struct()
+    m.ndim = 3
+    m.col_scale = 5
+    with pytest.raises(ValueError):
+        model.FlatModel(m)
+    m = model._new_struct()
+    m.ndim = 1
+    m.prior[0].lo, m.prior[0].hi, m.prior[0].kind, m.prior[0].sigma = 0., 1., _lib.PRIOR_GAUSSIAN, 0.0
+    with pytest.raises(ValueError):
+        model.FlatModel(m)
+    m = model._new_struct()
+    m.ndim, m.no_bsm, m.nbins, m.dimension = 1, 0, 20, 9
+    with pytest.raises(ValueError):
+        model.FlatModel(m)
+
+
+# ------------------------------------------------------------------ host containers
+def test_paramset_mirrors_reference_api():
+    ps = ParamSet([Param('a', 1., [0, 2], tag=ParamTag.SCALE, std=0.1),
+                   Param('b', 2., [0, 3], seed=[1, 2], prior=PriorsCateg.GAUSSIAN, std=0.5)])
+    assert ps.names == ('a', 'b') and ps.values == (1., 2.) and ps.ranges == ((0, 2), (0, 3))
+    assert ps.seeds == ((0, 2), (1, 2)) and ps.stds == (0.1, 0.5)
+    assert ps['b'].prior is PriorsCateg.GAUSSIAN and ps[0].prior is PriorsCateg.UNIFORM
+    assert ps.from_tag(ParamTag.SCALE, values=True) == (1.,)
+    assert ps.from_tag(ParamTag.SCALE, index=True, invert=True) == (1,)
+    assert len(ps.from_tag([ParamTag.SCALE, ParamTag.NONE])) == 2
+    assert ps[1].tag is ParamTag.NONE and ps[1].nominal_value == 2.
+    with pytest.raises(ValueError):
+        ParamSet([Param('a', 1., [0, 2]), Param('a', 1., [0, 2])])
+    assert len(ps.extend(Param('c', 0., [0, 1]))) == 3
+    assert ps.remove_params(ParamSet([ps[0]])).names == ('b',)
+    assert enums.Texture.OET.value == 2 and enums.ParamTag.BESTFIT.value == 6  # enums.py:28-63
+
+
+def test_flatten_resolves_columns_like_the_reference(golden):
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    s = fm.struct
+    assert s.ndim == 6 and s.no_bsm == 1 and list(s.col_sm) == [0, 1, 2, 3] and list(s.col_src) == [4, 5]
+    assert [s.prior[k].kind for k in range(6)] == [2, 2, 2, 0, 0, 0]
+    assert np.allclose(list(s.fr_bf), go.angles_to_fr(g['asimov_angles']), atol=1e-15) and s.smearing == 0.02
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'])
+    s = model.flatten(args, asimov, pset).struct
+    assert s.no_bsm == 0 and s.col_scale == 6 and list(s.col_mass) == [4, 5] and s.nbins == 20 and s.dimension == 6
+    assert np.allclose(list(s.fixed_np), model.TEXTURE_ANGLES['OET']) and list(s.col_np) == [-1] * 4
+    assert [s.prior[k].kind for k in range(7)] == [2, 2, 2, 0, 1, 1, 0]
+    # only four of the six SM names present -> NuFIT defaults on the BSM path (fr.py:425-435)
+    pset4 = ParamSet(scan.sm_paramset(with_mass=False) + [pset['logLam']])
+    s = model.flatten(args, asimov, pset4).struct
+    assert list(s.col_sm) == [-1] * 4 and list(s.col_mass) == [-1, -1] and s.col_scale == 4
+    # Texture.NONE needs the four MMANGLES
+    s = model.flatten(models.bsm_args(texture=Texture.NONE), asimov, models.bsm11_paramset()).struct
+    assert list(s.col_np) == [6, 7, 8, 9] and s.col_scale == 10
+    with pytest.raises(ValueError):
+        model.flatten(models.bsm_args(texture=Texture.NONE), asimov, pset)
+    with pytest.raises(ValueError):
+        model.flatten(argparse.Namespace(likelihood=enums.Likelihood.GOLEMFIT, source_ratio=[1, 2, 0]), asimov, pset)
+    assert np.allclose(model.binning_edges([6e4, 1e7, 20]), models.BINNING)
+
+
+def test_length_mismatch_raises_assertion_like_reference(golden):
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    with pytest.raises(AssertionError):
+        llh.lnprior([0.1, 0.2], pset)          # llh.py:67-71
+    with pytest.raises(AssertionError):
+        llh.ln_prob([0.1] * 5, args, asimov, pset)
+    with pytest.raises(AssertionError):
+        llh.triangle_llh([0.1] * 7, args, asimov, pset)
+
+
+def test_shard_range_partitions_exactly():
+    for count in (0, 1, 7, 10 ** 10 + 3):
+        for world in (1, 2, 3, 8):
+            parts = [scan.shard_range(count, r, world, first_index=5) for r in range(world)]
+            assert parts[0][0] == 5 and sum(n for _, n in parts) == count
+            for (a, n), (b, _) in zip(parts, parts[1:]):
+                assert a + n == b
+            assert max(n for _, n in parts) - min(n for _, n in parts) <= 1
+
+
+def test_ensemble_sampler_recovers_gaussian():
+    rng = np.random.RandomState(5)
+    mu, sig = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
+    calls = []
+
+    def lnp(t):
+        calls.append(t.shape)
+        return -0.5 * np.sum(((t - mu) / sig) ** 2, axis=-1)
+    s = mcmc.EnsembleSampler(40, 3, lnp, seed=11)
+    pos = None
+    for pos, lp, _ in s.sample(mu + rng.randn(40, 3), iterations=300):
+        pass
+    s.reset()
+    for _ in s.sample(pos, iterations=1500):
+        pass
+    assert s.chain.shape == (40, 1500, 3) and s.lnprobability.shape == (40, 1500)
+    flat = s.chain.reshape(-1, 3)   # walker-major, mcmc.py:44
+    assert np.allclose(flat.mean(0), mu, atol=0.15) and np.allclose(flat.std(0), sig, rtol=0.1)
+    assert 0.4 < s.acceptance_fraction.mean() < 0.8 and s.acor.shape == (3,)
+    # one vectorised call per half-ensemble (+ one full-ensemble call at the start of each sample())
+    assert calls.count((40, 3)) == 2 and calls.count((20, 3)) == 2 * 1800 and len(calls) == 3602
+    with pytest.raises(ValueError):
+        mcmc.EnsembleSampler(5, 3, lnp)
+    bad = mcmc.EnsembleSampler(8, 2, lambda t: np.full(len(t), np.nan))
+    with pytest.raises(ValueError):
+        next(bad.sample(np.zeros((8, 2)), iterations=1))
+
+
+def test_seeds_and_save_chains(tmp_path):
+    pset = models.bsm7_paramset()
+    np.random.seed(3)
+    p0 = mcmc.flat_seed(pset, 32)
+    box = np.array(pset.seeds)
+    assert p0.shape == (32, 7) and np.all(p0 >= box[:, 0]) and np.all(p0 <= box[:, 1])
+    assert mcmc.gaussian_seed(pset, 8).shape == (8, 7)
+    out = str(tmp_path / 'sub' / 'chain')
+    mcmc.save_chains(p0, out)
+    assert np.array_equal(np.load(out + '.npy'), p0)
+
+
+# ------------------------------------------------------------------ kernel arithmetic on the host harness
+def test_harness_notebook_lnprob_matches_reference_fixture(golden):
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    lnp, fr, st = hh.lnprob(fm, g['theta'])
+    ref = g['lnprob']
+    inside = np.isfinite(g['lnprior'])
+    assert np.array_equal(np.isneginf(lnp[~inside]), np.ones((~inside).sum(), bool))
+    assert np.all((st[~inside] & _lib.ST_OUT_OF_PRIOR) != 0) and np.all(st[inside] == 0)
+    assert np.abs(fr[inside] - g['fr'][inside]).max() < 1e-12
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lnp), fin)          # incl. the pdf-underflow -> -inf emulation
+    assert np.max(np.abs(lnp[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-10
+    assert abs(lnp[0] - (-458.6843569885842)) < 1e-9 * 458   # SURVEY 8c spot value
+
+
+def test_harness_lnprior_matches_scipy_fixture(golden):
+    g = golden('ref_llh.npz')
+    fm = model.flatten(argparse.Namespace(source_ratio=[1, 2, 0], dimension=6, texture=Texture.OET,
+                                          binning=models.BINNING, no_bsm=False), None, models.bsm7_paramset(),
+                       likelihood='FLAT')
+    got = hh.lnprior(fm, g['theta7'])
+    ref = g['lnprior7']
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-12
+
+
+def test_harness_flux_averaged_fr_matches_reference_and_mpmath(golden):
+    g = golden('ref_flux.npz')
+    worst_mp, worst_ref = 0.0, 0.0
+    for tex in ('OET', 'OUT', 'OEU', 'NONE'):
+        for dim in (3, 6):
+            for src in ((1, 2, 0), (1, 0, 0), (0, 1, 0)):
+                sel = (g['tex'] == tex) & (g['dim'] == dim) & np.all(g['src'] == np.array(src, float), axis=1)
+                if not sel.any():
+                    continue
+                fm = model.flatten(models.bsm_args(dim, Texture.NONE, src), None, models.bsm11_paramset(dim), likelihood='FLAT')
+                fr, st = hh.fr(fm, g['theta'][sel])
+                assert not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+                worst_mp = max(worst_mp, np.abs(fr - g['fr_mp'][sel]).max())
+                ok = g['ok'][sel]   # points where the reference passed its own unitarity assertion
+                # the reference's own error vs mpmath on those points bounds what can be asked of parity
+                ref_err = np.abs(g['fr'][sel][ok] - g['fr_mp'][sel][ok]).max(axis=1)
+                good = ref_err < 1e-11
+                worst_ref = max(worst_ref, np.abs(fr[ok][good] - g['fr'][sel][ok][good]).max())
+                if tex != 'NONE':  # same answer through the fixed-texture (constant T) path
+                    fm7 = model.flatten(models.bsm_args(dim, Texture[tex], src), None, models.bsm7_paramset(dim), likelihood='FLAT')
+                    th7 = np.delete(g['theta'][sel], [6, 7, 8, 9], axis=1)
+                    fr7, _ = hh.fr(fm7, th7)
+                    assert np.abs(fr7 - fr).max() < 1e-13
+    assert worst_mp < 1e-10, worst_mp     # vs mpmath truth, everywhere (abs. error on a unit-sum composition)
+    assert worst_ref < 1e-10, worst_ref   # vs the reference where the reference itself is accurate
+
+
+def test_harness_eigen_stage_against_lapack_on_random_bsm_points():
+    rng = np.random.default_rng(7)
+    n = 4000
+    worst = 0.0
+    nfast = 0
+    for texname in ('OET', 'OUT', 'OEU', 'NONE'):
+        for dim in (3, 5, 6, 8):
+            pset = models.bsm11_paramset(dim)
+            th = models.draw_in_ranges(pset, n, rng, seeds=True)
+            lo, hi = model.SCALE_BOUNDARIES[dim]
+            th[:, 10] = rng.uniform(lo, hi, n)
+            if texname == 'NONE':
+                th[:, 6:9] = rng.uniform(0, 1, (n, 3))
+                th[:, 9] = rng.uniform(0, 2 * np.pi, n)
+            else:
+                th[:, 6:10] = model.TEXTURE_ANGLES[texname]
+            fm = model.flatten(models.bsm_args(dim, Texture.NONE), None, pset, likelihood='FLAT')
+            fr, st = hh.fr(fm, th)
+            ref = truth.eigh_flux_averaged_fr(th[:, :4], th[:, 4:6], th[:, 6:10], th[:, 10], dim, models.BINNING,
+                                              np.array([1, 2, 0.]) / 3)
+            assert not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+            err = np.abs(fr - ref).max(axis=1)
+            worst = max(worst, err.max())
+            nfast += np.count_nonzero((st & _lib.ST_REFINED) == 0)
+    assert worst < 1e-10, worst
+    assert nfast > 0.5 * 16 * n   # the closed-form path must carry the bulk of the points
+
+
+def test_harness_prior_draws_follow_philox_convention():
+    fm = scan.scan_model('unitary')
+    th = hh.draw(fm, 26, 12345, 1000)
+    u = go.philox_uniforms(26, 12345, 1000, block=0)
+    assert np.array_equal(th[:, :3], u[:, :3])                      # U(0,1) ranges: theta == uniform
+    assert np.allclose(th[:, 3], 2 * np.pi * u[:, 3], rtol=1e-15)
+    th2 = hh.draw(fm, 26, 12345 + 500, 500)
+    assert np.array_equal(th2, th[500:])                            # counter = global index: shard-invariant
+    big = hh.draw(fm, 26, (1 << 32) - 2, 4)                         # index crosses 2^32
+    assert np.array_equal(big[:, :3], go.philox_uniforms(26, (1 << 32) - 2, 4)[:, :3])
+
+
+def test_harness_histogram_is_bit_exact_np_histogramdd():
+    rng = np.random.default_rng(3)
+    fr = rng.dirichlet([1, 1, 1], 100000)
+    fr[:300, 0] = np.arange(300) / 26.0
+    fr[300:600, 1] = np.arange(300) * (1.0 / 26.0)
+    fr[600:900, 2] = np.nextafter(np.arange(300) / 201.0, 0)
+    fr[900:905] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1.0000000001, 0, 0], [np.nan, 0.5, 0.5]]
+    for nb in (0, 1, 25, 125, 200):
+        assert np.array_equal(hh.hist(fr, nb), go.ternary_histogram(fr, nb)), nb
