@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the log-posterior hot path (driver contract: one JSON line on stdout).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json config 3, the BSM fit the north star's roofline target names): the batched
+BSM dim-6 / texture-OET log-posterior -- 6 SM parameters + log10(Lambda) per point, 20 energy bins,
+Gaussian flavor-ratio likelihood + (truncated-)Gaussian priors -- on a synthetic batch of
+4096 walkers x 1024 independent chains = 2^22 parameter points per step and per GPU (theta is
+235 MB, larger than the 126 MB L2, so every step streams its input from HBM).  One step = one pass of
+the hot path over that batch = ONE kernel launch.
+
+  value    : log-posterior evaluations / s over all ranks, theta resident in HBM (CUDA events on the
+             launching stream, barrier + synchronize on both sides, max over ranks)
+  e2e      : same metric through the public host API (`llh.LnProb.evaluate_host` -> C ABI
+             `gf_lnprob_host`): pinned host theta -> chunked H2D -> kernel -> D2H of the results
+  roofline : algorithmic fp64 FLOPs (9252 per evaluation) / kernel time, against the
+             fp64 FMA peak MEASURED in the same run by a DFMA microbenchmark (MEASURED_PEAKS.json
+             carries no fp64 figure); HBM traffic is reported alongside
+  scan     : secondary section -- the sharded Monte-Carlo scan (config 4), whole-job samples / s
+             including the NCCL all-reduce of the histograms
+  cpu_baseline : the oracle's scalar float128 ln_prob (port of the reference path) on 1 host core
+
+`--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure
+Python and cannot travel to the GPU box) on all host cores for the same metric and config.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+FLOP_PER_EVAL = 9252          # F_BSM for D=7, G=5, 20 bins
+BYTES_PER_EVAL = 64           # 7 doubles in, 1 out
+WALKERS, CHAINS = 4096, 1024
+METRIC = 'log-posterior evals/sec'
+WORKLOAD = ('C3: BSM dim-6 operator, texture OET, 6 SM params + logLambda, 20 energy bins, Gaussian flavor-ratio LLH '
+            '+ priors; 4096 walkers x 1024 chains = 4194304 points per step per GPU')
+
+
+def build_problem():
+    import models
+    from golemflavor_b200.enums import Texture
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+    return models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET), models
+
+
+def synth_theta(pset, n, seed, models):
+    """Uniform inside Param.ranges for the SM block (SURVEY 8d 'throughput batches'), logLam across
+    the dim-6 scale boundaries."""
+    rng = np.random.default_rng(seed)
+    return models.draw_in_ranges(pset, n, rng)
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        busy = [s for s, p in zip(sm, power) if p >= 0.6 * max(power)] if power else sm
+        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def _cpu_eval_chunk(job):
+    """Scalar float128 ln_prob of the oracle (restatement of llh.py:121-130 + fr.py) on a chunk."""
+    seed, count = job
+    import models  # noqa: F401  (sys.path set at import)
+    from oracle import golem_oracle as go
+    (args, asimov, pset), _ = build_problem()
+    theta = synth_theta(pset, count, seed, sys.modules['models'])
+    t0 = time.perf_counter()
+    out = []
+    for t in theta:
+        try:
+            out.append(go.ln_prob(list(t), args, asimov, pset))
+        except AssertionError:   # the reference's unitarity assertion (fr.py:493-498): same work was done
+            out.append(np.nan)
+    return time.perf_counter() - t0, count, float(np.sum(np.isfinite(out)))
+
+
+def cpu_baseline(per_core, cores):
+    jobs = [(1000 + c, per_core) for c in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_eval_chunk(jobs[0])]
+    else:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(cores) as pool:
+            res = pool.map(_cpu_eval_chunk, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[1] for r in res)
+    compute = max(r[0] for r in res)
+    return total / compute, total, wall
+
+
+def run_reference(opts):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = 150
+    for _ in range(max(0, min(opts.warmup, 1))):
+        cpu_baseline(8, cores)
+    vals = []
+    t0 = time.perf_counter()
+    steps = max(1, min(opts.steps, 3))
+    for _ in range(steps):
+        v, total, _ = cpu_baseline(per_core, cores)
+        vals.append(v)
+    elapsed = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    sample = '{0} scalar float128 ln_prob evaluations per step ({1} per process x {2} processes), same model and synthetic theta ' \
+             'distribution as the GPU arm'.format(per_core * cores, per_core, cores)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': opts.gpus, 'steps': steps,
+        'warmup': min(opts.warmup, 1), 'ms_per_step': 1e3 * elapsed / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f80 (x87 long double, as the reference)', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(opts):
+    import torch
+    import torch.distributed as dist
+    from golemflavor_b200 import _lib, llh, scan
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    (args, asimov, pset), models = build_problem()
+    fn = llh.LnProb(args, asimov, pset)
+    n = WALKERS * CHAINS
+    theta_host = torch.as_tensor(synth_theta(pset, n, 25 + rank, models)).pin_memory()
+    theta = theta_host.cuda()
+    out = torch.empty(n, dtype=torch.float64, device='cuda')
+    stream = _lib.stream_ptr(torch)
+
+    def step():
+        _lib.check(lib.gf_lnprob(fn.model.ref, _lib.ptr(theta), n, fn.ndim, 1, _lib.ptr(out), None, None, stream))
+
+    # -- fp64 peak probe (same run, same clocks)
+    sink = torch.zeros(8, dtype=torch.float64, device='cuda')
+    import ctypes as C
+    flops = C.c_double()
+    peak = 0.0
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.gf_fp64_peak_probe(200000, _lib.ptr(sink), C.byref(flops), stream))
+        e1.record()
+        torch.cuda.synchronize()
+        peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+
+    # -- device-resident throughput
+    for _ in range(opts.warmup):
+        step()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = lib.gf_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(opts.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lib.gf_launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clock_info = clocks.stop() if rank == 0 else None
+    value = world * n * opts.steps / (ms * 1e-3)
+    kernel_ms = ms / opts.steps
+
+    # -- end to end through the host API
+    out_host = torch.empty(n, dtype=torch.float64).pin_memory()
+    th_np, out_np = theta_host.numpy(), out_host.numpy()
+    e2e_steps = max(3, min(opts.steps, 10))
+    for _ in range(2):
+        fn.evaluate_host(th_np, out=out_np)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fn.evaluate_host(th_np, out=out_np)     # returns after the results are in host memory
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * e2e_steps / e2e_s
+    assert np.array_equal(out_np, out.cpu().numpy()), 'host pipeline and device path disagree'
+    finite_frac = float(np.isfinite(out_np).mean())
+
+    # -- secondary: sharded Monte-Carlo scan with the histogram all-reduce (config 4)
+    scan_info = None
+    if opts.scan_samples > 0:
+        fm = scan.scan_model(opts.scan_mode, dimension=6)
+        scan.scan_histogram(fm, 10 ** 7, nb=25, seed=26)      # warm-up (also NCCL channel set-up)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        hist, kept = scan.scan_histogram(fm, opts.scan_samples, nb=25, seed=26, return_tensor=True)
+        s1.record()
+        barrier()
+        scan_ms = max_over_ranks(s0.elapsed_time(s1))
+        scan_info = {'mode': opts.scan_mode, 'samples': opts.scan_samples, 'nb': 25, 'seconds': scan_ms * 1e-3,
+                     'samples_per_s': opts.scan_samples / (scan_ms * 1e-3), 'scaling': 'strong',
+                     'kept': int(kept.item()), 'hist_checksum': int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item()),
+                     'collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
+
+    if rank == 0:
+        base = None
+        if world == 1 and opts.cpu_evals > 0:
+            v, total, wall = cpu_baseline(opts.cpu_evals, 1)
+            base = {'value': v, 'unit': 'evals/s', 'cores': 1, 'kind': 'port',
+                    'sample': '{0} scalar float128 ln_prob evaluations of the same model ({1:.1f} s)'.format(total, wall)}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = peaks.get('hbm_gbs', 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('k_lnprob_bytes_per_launch')
+        except (OSError, ValueError):
+            pass
+        achieved = FLOP_PER_EVAL * n / (kernel_ms * 1e-3) / 1e12
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': opts.steps, 'warmup': opts.warmup,
+            'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'points_per_step_per_gpu': n, 'ndim': fn.ndim, 'nbins': 20, 'parallelism': 'dp%d (independent shards, no data-path collective)' % world,
+                       'l2': 'inputs (235 MB theta per step) larger than the 126 MB L2', 'finite_fraction': finite_frac},
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
+                         'traffic': traffic, 'kernel': 'k_lnprob<0>', 'flop_per_eval': FLOP_PER_EVAL,
+                         'peak_source': 'DFMA microbenchmark (gf_fp64_peak_probe) measured in this run; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2',
+                         'hbm': {'achieved': BYTES_PER_EVAL * n / (kernel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                                 'frac': BYTES_PER_EVAL * n / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
+            'cpu_baseline': base,
+            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': n * fn.ndim * 8, 'd2h_bytes_per_step': n * 8,
+                    'steps': e2e_steps, 'api': 'golemflavor_b200.llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)'},
+            'gpu_launches': int(launches),
+            'clocks': clock_info,
+            'scan': scan_info,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=400)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cpu-evals', type=int, default=1500, help='size of the bounded CPU-baseline sample (0 = skip)')
+    ap.add_argument('--scan-samples', type=int, default=10 ** 10, help='samples of the secondary scan section (0 = skip)')
+    ap.add_argument('--scan-mode', default='anarchic', choices=['unitary', 'x', 'texture', 'anarchic'])
+    opts = ap.parse_args()
+    opts.warmup = max(opts.warmup, 3) if opts.impl == 'b200' else opts.warmup
+    if opts.impl == 'reference':
+        run_reference(opts)
+    else:
+        run_gpu(opts)
+
+
+if __name__ == '__main__':
+    main()

@@ -91,6 +91,7 @@ _SIGNATURES = {
     'gf_scan_hist': (C.c_int, [C.POINTER(Model), C.POINTER(ScanConfig), _P, _P, _P]),
     'gf_scan_samples': (C.c_int, [C.POINTER(Model), C.POINTER(ScanConfig), _P, _P, _P, _P]),
     'gf_ternary_hist': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    'gf_selftest_math': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     'gf_fp64_peak_probe': (C.c_int, [C.c_int64, _P, C.POINTER(C.c_double), _P]),
 }
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -91,6 +91,8 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
     d->llh_kind = m->llh_kind;
     GF_REQUIRE(m->llh_kind == GF_LLH_FLAT || m->llh_kind == GF_LLH_GAUSSIAN, "model.llh_kind = %d is not a GF_LLH_* value", m->llh_kind);
     d->emulate_underflow = m->emulate_underflow ? 1 : 0;
+    static const double wpoly[GFP_W_POLY_N] = GFP_W_POLY_INIT;
+    memcpy(d->wpoly, wpoly, sizeof(wpoly));
 
     struct { const int32_t* src; int32_t* dst; int n; const char* name; } cols[] = {
         {m->col_sm, d->col_sm, 4, "col_sm"},       {m->col_mass, d->col_mass, 2, "col_mass"},
@@ -329,7 +331,24 @@ __global__ void __launch_bounds__(GF_PROBE_THREADS) k_fp64_probe(int64_t iters, 
     if (s == 12345.6789) sink[0] = s; /* never true: keeps the chains alive */
 }
 
+__global__ void __launch_bounds__(GF_EW_THREADS) k_selftest_math(const double* __restrict__ x, int64_t n, double* __restrict__ rs, double* __restrict__ rc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rs[i] = gfp_rsqrt(x[i]);
+    rc[i] = gfp_rcp(x[i]);
+}
+
 /* ------------------------------------------------------------------ C ABI */
+
+extern "C" int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* d_rcp_out, void* stream) {
+    GF_REQUIRE(n >= 0, "gf_selftest_math: n = %lld", (long long)n);
+    if (n == 0) return GF_OK;
+    GF_REQUIRE(d_x && d_rsqrt_out && d_rcp_out, "gf_selftest_math: null pointer");
+    k_selftest_math<<<gf_blocks_for(n, GF_EW_THREADS), GF_EW_THREADS, 0, (cudaStream_t)stream>>>(d_x, n, d_rsqrt_out, d_rcp_out);
+    ++g_gf_launches;
+    GF_LAUNCH_CHECK("k_selftest_math");
+    return GF_OK;
+}
 
 extern "C" int gf_angles_to_u(const double* d_angles, int64_t n, double* d_u, void* stream) {
     GF_REQUIRE(n >= 0, "gf_angles_to_u: n = %lld", (long long)n);

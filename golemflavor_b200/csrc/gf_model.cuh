@@ -18,6 +18,7 @@ struct gf_dev_model {
     int32_t col_sm[4], col_mass[2], col_src[2], col_np[4], col_scale, col_x;
     double fixed_sm[4], fixed_mass[2], fixed_src[3], fixed_np[4], fixed_loglam;
     gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
+    double wpoly[GFP_W_POLY_N]; /* cos(phi/3) polynomial, direct constant-bank operands  */
     double g[GF_MAX_BINS];      /* 2 Ec^(dim-2) 2^70: H*2E = H0 + 10^logLam g T          */
     double width[GF_MAX_BINS];  /* |E_hi - E_lo|                          (fr.py:414)    */
     double fr_bf[3];
@@ -89,7 +90,9 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         fr[2] = f[2] * inv;
     } else {
         const gfp_cols12 u = gfp_cols_from_trig(t);
-        const gfp_herm3 h0 = gfp_herm_from_cols(u, q.mass[0] * GFP_MASS_SCALE, q.mass[1] * GFP_MASS_SCALE);
+        /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
+         * the polynomial invariants of the pencil H0 + rho T */
+        gfp_herm3 h0 = gfp_herm_from_cols(u, q.mass[0] * GFP_MASS_SCALE, q.mass[1] * GFP_MASS_SCALE);
         gfp_herm3 T;
         if (m.np_free) {
             const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
@@ -97,40 +100,39 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         } else {
             T = m.T;
         }
+        const gfp_pencil pen = gfp_make_pencil(h0, T);
 #ifdef __CUDA_ARCH__
         const double lam = exp10(q.loglam);
 #else
         const double lam = pow(10.0, q.loglam);
 #endif
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const double S = q.src[0] + q.src[1] + q.src[2];
+        const double sd0 = q.src[0] - q.src[2], sd1 = q.src[1] - q.src[2];
+        double a0 = 0.0, a1 = 0.0, wsum = 0.0;
         for (int b = 0; b < m.nbins; ++b) {
             const double rho = lam * m.g[b];
-            gfp_herm3 h;
-            h.d0 = fma(rho, T.d0, h0.d0);
-            h.d1 = fma(rho, T.d1, h0.d1);
-            h.d2 = fma(rho, T.d2, h0.d2);
-            h.ar = fma(rho, T.ar, h0.ar);
-            h.ai = fma(rho, T.ai, h0.ai);
-            h.br = fma(rho, T.br, h0.br);
-            h.bi = fma(rho, T.bi, h0.bi);
-            h.cr = fma(rho, T.cr, h0.cr);
-            h.ci = fma(rho, T.ci, h0.ci);
-            st |= gfp_herm3_abs2(h, X);
-            double f[3];
-            gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
+            gfp_x4 x;
+            if (!gfp_pencil_x4_fast(m.wpoly, pen, rho, x)) {
+                gfp_x4 slow; /* separate object: keeps the fast path's x in registers */
+                st |= gfp_pencil_x4_jacobi(&h0, &T, rho, &slow);
+                x = slow;
+            }
+            double f0, f1;
+            gfp_mix4(x, q.src[2], sd0, sd1, S, f0, f1);
             const double wd = m.width[b];
-            a0 = fma(wd, f[0], a0);
-            a1 = fma(wd, f[1], a1);
-            a2 = fma(wd, f[2], a2);
-            /* |V|^2 must be a doubly stochastic matrix: a negative entry beyond epsilon is the
-             * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
-            const double mn = fmin(fmin(fmin(X[0], X[1]), fmin(X[2], X[3])), fmin(fmin(X[4], X[5]), fmin(fmin(X[6], X[7]), X[8])));
-            if (!(mn >= -m.epsilon)) st |= GFP_ST_NON_UNITARY;
+            a0 = fma(wd, f0, a0);
+            a1 = fma(wd, f1, a1);
+            wsum += wd;
         }
-        const double inv = 1.0 / (a0 + a1 + a2);
+        /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is 1 / (S sum(width)) */
+        const double inv = 1.0 / (S * wsum);
         fr[0] = a0 * inv;
         fr[1] = a1 * inv;
-        fr[2] = a2 * inv;
+        fr[2] = 1.0 - fr[0] - fr[1];
+        /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
+         * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
+        const double mn = fmin(fr[0], fmin(fr[1], fr[2]));
+        if (!(mn >= -m.epsilon)) st |= GFP_ST_NON_UNITARY;
     }
     if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
     return st;
@@ -170,16 +172,11 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
         st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;
         return (lp != lp) ? NAN : -INFINITY;
     }
-    if (m.llh_kind == GF_LLH_FLAT) {
-        /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
-        gf_point q;
-        gf_resolve_point(m, get, q);
-        st = gf_point_fr(m, q, fr);
-        return lp + m.llh_const;
-    }
     gf_point q;
     gf_resolve_point(m, get, q);
     st = gf_point_fr(m, q, fr);
+    /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
+    if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
     return lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
 }
 

@@ -198,6 +198,9 @@ int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsign
 /* DFMA microbenchmark: runs `iters` dependent-chain FMAs x `chains` per thread on a full grid and
  * returns the number of fp64 FLOPs issued (2 per FMA) in *flops; time it with CUDA events on `stream`. */
 int gf_fp64_peak_probe(int64_t iters, double* d_sink /*[>= 1]*/, double* flops, void* stream);
+/* Device self-test of the MUFU-seeded helpers of the eigen stage: rsqrt_out[i] ~ 1/sqrt(x[i]),
+ * rcp_out[i] ~ 1/x[i] for normal positive x (tests/test_gpu_parity.py checks them to 1e-15). */
+int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* d_rcp_out, void* stream);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t gf_launch_count(void);
 

@@ -84,6 +84,6 @@ def eig(ham):
     h = np.ascontiguousarray(np.asarray(ham, dtype=np.complex128)).reshape(-1, 3, 3)
     n = h.shape[0]
     hv = h.view(np.float64).reshape(n, 18)
-    lam, vec, xf, ok = np.empty((n, 3)), np.empty((n, 18)), np.empty((n, 9)), np.empty(n, dtype=np.uint8)
+    lam, vec, xf, ok = np.empty((n, 3)), np.empty((n, 18)), np.empty((n, 4)), np.empty(n, dtype=np.uint8)
     load().hh_eig(_p(hv), C.c_int64(n), _p(lam), _p(vec), _p(xf), _p(ok))
-    return lam, vec.view(np.complex128).reshape(n, 3, 3), xf.reshape(n, 3, 3), ok.astype(bool)
+    return lam, vec.view(np.complex128).reshape(n, 3, 3), xf.reshape(n, 2, 2), ok.astype(bool)

@@ -72,13 +72,16 @@ extern "C" void hh_hist(const double* fr, int64_t n, int nb, unsigned long long*
     }
 }
 
-extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, double* vec, double* x_fast, uint8_t* fast_ok) {
+extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, double* vec, double* x_fast /*[n][4]*/, uint8_t* fast_ok) {
+    static const double wpoly[GFP_W_POLY_N] = GFP_W_POLY_INIT;
     for (int64_t i = 0; i < n; ++i) {
         const double* h = ham + 18 * i;
         gfp_herm3 m;
         m.d0 = h[0]; m.d1 = h[8]; m.d2 = h[16];
         m.ar = h[2]; m.ai = h[3]; m.br = h[4]; m.bi = h[5]; m.cr = h[10]; m.ci = h[11];
         gfp_herm3_eig_sorted(m, lam + 3 * i, vec + 18 * i);
-        fast_ok[i] = gfp_herm3_abs2_fast(m, x_fast + 9 * i) ? 1 : 0;
+        gfp_x4 x = {NAN, NAN, NAN, NAN};
+        fast_ok[i] = gfp_herm3_x4_fast(wpoly, m, x) ? 1 : 0;
+        x_fast[4 * i] = x.x00; x_fast[4 * i + 1] = x.x01; x_fast[4 * i + 2] = x.x10; x_fast[4 * i + 3] = x.x11;
     }
 }
