@@ -63,44 +63,53 @@ def synth_theta(pset, n, seed, models):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-              'clocks_event_reasons.sw_power_cap')
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every 5 ms from a
+    background thread while the timed region runs (the main thread sits in a CUDA synchronize,
+    which releases the GIL)."""
+    BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4,
+           'hw_power_brake_slowdown': 0x80}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self._stop, self.thread, self.err = index, [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(visible.split(',')[index]) if visible and visible.split(',')[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # noqa: BLE001
+            self.nv, self.err = None, repr(exc)
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.rows.append((sm, pw, rs))
+            except Exception as exc:  # noqa: BLE001
+                self.err = repr(exc)
+                break
+            time.sleep(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for nm, v in zip(names, r[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
-        busy = [s for s, p in zip(sm, power) if p >= 0.6 * max(power)] if power else sm
-        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
-                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+        if self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['clock sampling unavailable: %s' % self.err]}
+        self._stop.set()
+        self.thread.join()
+        sm = [r[0] for r in self.rows]
+        power = [r[1] for r in self.rows]
+        reasons = sorted(name for name, bit in self.BAD.items() if any(r[2] & bit for r in self.rows))
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_min_mhz': min(sm) if sm else None, 'sm_max_mhz': self.max_sm,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': reasons}
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
@@ -213,7 +222,7 @@ def run_gpu(opts):
     for _ in range(4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(lib.gf_fp64_peak_probe(200000, _lib.ptr(sink), C.byref(flops), stream))
+        _lib.check(lib.gf_fp64_peak_probe(0, 200000, _lib.ptr(sink), C.byref(flops), stream))
         e1.record()
         torch.cuda.synchronize()
         peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)

@@ -19,7 +19,8 @@ PRIOR_UNIFORM, PRIOR_GAUSSIAN, PRIOR_LIMITEDGAUSS = 0, 1, 2
 LLH_FLAT, LLH_GAUSSIAN = 0, 1
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'lib')
-LIB_PATH = os.path.join(LIB_DIR, 'libgolemflavor_b200.so')
+# GOLEMFLAVOR_B200_LIB: developer override used to A/B kernel build variants (scratch/variants)
+LIB_PATH = os.environ.get('GOLEMFLAVOR_B200_LIB') or os.path.join(LIB_DIR, 'libgolemflavor_b200.so')
 
 
 class GolemFlavorError(RuntimeError):
@@ -92,7 +93,7 @@ _SIGNATURES = {
     'gf_scan_samples': (C.c_int, [C.POINTER(Model), C.POINTER(ScanConfig), _P, _P, _P, _P]),
     'gf_ternary_hist': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
     'gf_selftest_math': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
-    'gf_fp64_peak_probe': (C.c_int, [C.c_int64, _P, C.POINTER(C.c_double), _P]),
+    'gf_fp64_peak_probe': (C.c_int, [C.c_int32, C.c_int64, _P, C.POINTER(C.c_double), _P]),
 }
 EXPORTS = tuple(sorted(_SIGNATURES))
 

@@ -312,22 +312,37 @@ __global__ void __launch_bounds__(GF_EW_THREADS)
     llh[i] = gf_multi_gaussian(f, bf, half_inv_s2, lognorm3, offset, emulate_underflow, underflow_logpdf);
 }
 
-/* DFMA throughput probe: 8 independent dependent-chains per thread, nothing else in the loop. */
+/* fp64 throughput probes: 8 independent dependent-chains per thread, nothing else in the loop.
+ *   mode 0: a = fma(a, m, b)      m, b uniform constants (2 register-file operands)  -- the roofline peak
+ *   mode 1: a = fma(a, b_c, d_c)  three distinct per-thread register pairs per instruction
+ *   mode 2: a = a * b_c           DMUL, two distinct register pairs
+ *   mode 3: a = fma(a, b, d)      b, d per-thread registers shared by all chains (operand-reuse friendly)
+ */
 #define GF_PROBE_CHAINS 8
 #define GF_PROBE_THREADS 256
 #define GF_PROBE_BLOCKS_PER_SM 8
+template <int MODE>
 __global__ void __launch_bounds__(GF_PROBE_THREADS) k_fp64_probe(int64_t iters, double seed, double* __restrict__ sink) {
-    double a[GF_PROBE_CHAINS];
+    double a[GF_PROBE_CHAINS], b[GF_PROBE_CHAINS], d[GF_PROBE_CHAINS];
 #pragma unroll
-    for (int c = 0; c < GF_PROBE_CHAINS; ++c) a[c] = seed + 1e-3 * (threadIdx.x + c);
-    const double m = 1.0 - 1e-9, b = 1e-9;
+    for (int c = 0; c < GF_PROBE_CHAINS; ++c) {
+        a[c] = seed + 1e-3 * (threadIdx.x + c);
+        b[c] = 1.0 - 1e-9 * (1 + ((threadIdx.x + c) & 7)) * seed * 2.0; /* per-thread values: stay in registers */
+        d[c] = 1e-9 * (1 + ((threadIdx.x * 3 + c) & 7)) * seed * 2.0;
+    }
+    const double m = 1.0 - 1e-9, k = 1e-9;
     for (int64_t it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int c = 0; c < GF_PROBE_CHAINS; ++c) a[c] = fma(a[c], m, b);
+        for (int c = 0; c < GF_PROBE_CHAINS; ++c) {
+            if (MODE == 0) a[c] = fma(a[c], m, k);
+            if (MODE == 1) a[c] = fma(a[c], b[c], d[c]);
+            if (MODE == 2) a[c] = a[c] * b[c];
+            if (MODE == 3) a[c] = fma(a[c], b[0], d[0]);
+        }
     }
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < GF_PROBE_CHAINS; ++c) s += a[c];
+    for (int c = 0; c < GF_PROBE_CHAINS; ++c) s += a[c] + b[c] + d[c];
     if (s == 12345.6789) sink[0] = s; /* never true: keeps the chains alive */
 }
 
@@ -424,14 +439,20 @@ extern "C" int gf_multi_gaussian(const double* d_fr, int64_t n, const double* h_
     return GF_OK;
 }
 
-extern "C" int gf_fp64_peak_probe(int64_t iters, double* d_sink, double* flops, void* stream) {
+extern "C" int gf_fp64_peak_probe(int32_t mode, int64_t iters, double* d_sink, double* flops, void* stream) {
     GF_REQUIRE(iters > 0 && d_sink != nullptr, "gf_fp64_peak_probe: bad arguments");
+    GF_REQUIRE(mode >= 0 && mode <= 3, "gf_fp64_peak_probe: mode = %d outside [0, 3]", mode);
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
     const unsigned blocks = (unsigned)(sms * GF_PROBE_BLOCKS_PER_SM);
-    k_fp64_probe<<<blocks, GF_PROBE_THREADS, 0, (cudaStream_t)stream>>>(iters, 0.5, d_sink);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode == 0) k_fp64_probe<0><<<blocks, GF_PROBE_THREADS, 0, st>>>(iters, 0.5, d_sink);
+    if (mode == 1) k_fp64_probe<1><<<blocks, GF_PROBE_THREADS, 0, st>>>(iters, 0.5, d_sink);
+    if (mode == 2) k_fp64_probe<2><<<blocks, GF_PROBE_THREADS, 0, st>>>(iters, 0.5, d_sink);
+    if (mode == 3) k_fp64_probe<3><<<blocks, GF_PROBE_THREADS, 0, st>>>(iters, 0.5, d_sink);
     ++g_gf_launches;
     GF_LAUNCH_CHECK("k_fp64_probe");
-    if (flops) *flops = 2.0 * (double)iters * GF_PROBE_CHAINS * GF_PROBE_THREADS * (double)blocks;
+    /* flops: 2 per FMA, 1 per MUL */
+    if (flops) *flops = (mode == 2 ? 1.0 : 2.0) * (double)iters * GF_PROBE_CHAINS * GF_PROBE_THREADS * (double)blocks;
     return GF_OK;
 }

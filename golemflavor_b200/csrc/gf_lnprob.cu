@@ -18,11 +18,14 @@
 extern std::atomic<unsigned long long> g_gf_launches;
 
 #define GF_LP_THREADS 128
+#ifndef GF_LP_MIN_BLOCKS
+#define GF_LP_MIN_BLOCKS 4 /* resident blocks per SM the register allocation is tuned for */
+#endif
 
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 
 template <int KIND>
-__global__ void __launch_bounds__(GF_LP_THREADS)
+__global__ void __launch_bounds__(GF_LP_THREADS, GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -195,9 +195,12 @@ int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_
 int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsigned long long* d_hist, void* stream);
 
 /* ---- measurement helper ----------------------------------------------- */
-/* DFMA microbenchmark: runs `iters` dependent-chain FMAs x `chains` per thread on a full grid and
- * returns the number of fp64 FLOPs issued (2 per FMA) in *flops; time it with CUDA events on `stream`. */
-int gf_fp64_peak_probe(int64_t iters, double* d_sink /*[>= 1]*/, double* flops, void* stream);
+/* fp64 throughput microbenchmarks: `iters` dependent FMAs x 8 chains per thread on a full grid;
+ * *flops receives the number of fp64 FLOPs issued (2 per FMA, 1 per MUL); time it with CUDA events
+ * on `stream`.  mode 0 (operands: 1 register pair + uniform constants) is the roofline peak;
+ * modes 1-3 probe the register-file operand bandwidth (3 distinct register pairs per DFMA,
+ * DMUL with 2 register pairs, DFMA with operands shared between consecutive instructions). */
+int gf_fp64_peak_probe(int32_t mode, int64_t iters, double* d_sink /*[>= 1]*/, double* flops, void* stream);
 /* Device self-test of the MUFU-seeded helpers of the eigen stage: rsqrt_out[i] ~ 1/sqrt(x[i]),
  * rcp_out[i] ~ 1/x[i] for normal positive x (tests/test_gpu_parity.py checks them to 1e-15). */
 int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* d_rcp_out, void* stream);
