@@ -21,7 +21,7 @@ from .enums import ParamTag, PriorsCateg, Texture, enum_name
 from .param import Param, ParamSet
 
 __all__ = ['sm_paramset', 'scan_paramset', 'scan_model', 'scan_histogram', 'scan_samples', 'ternary_histogram',
-           'shard_range']
+           'shard_range', 'allreduce_counts']
 
 DEFAULT_BINNING = np.logspace(np.log10(6e4), np.log10(1e7), 21)  # fr.py:283-285
 
@@ -109,6 +109,17 @@ def _dist():
     return None
 
 
+def allreduce_counts(*tensors):
+    """Sum integer count tensors over the ranks of the initialised process group in place
+    (NCCL on GPUs; any backend works -- the gloo CPU tests exercise exactly this call).  No-op
+    without a process group.  This is the ONLY collective of the scan path."""
+    dist = _dist()
+    if dist is not None and dist.get_world_size() > 1:
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return tensors
+
+
 def scan_histogram(fm, count, nb=25, seed=26, first_index=0, distributed=True, out=None, return_tensor=False):
     """Histogram of ``count`` prior samples: ``np.histogramdd(frs, bins=(nb+1,)*3, range=((0,1),)*3)``.
 
@@ -125,8 +136,7 @@ def scan_histogram(fm, count, nb=25, seed=26, first_index=0, distributed=True, o
     cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=int(nb))
     _lib.check(_lib.load().gf_scan_hist(fm.ref, C.byref(cfg), _lib.ptr(hist), _lib.ptr(kept), _lib.stream_ptr(torch)))
     if dist and world > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-        dist.all_reduce(kept, op=dist.ReduceOp.SUM)
+        allreduce_counts(hist, kept)
     h = hist.reshape(nb + 1, nb + 1, nb + 1)
     if return_tensor:
         return h, kept
