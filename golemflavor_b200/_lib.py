@@ -68,6 +68,11 @@ class ScanConfig(C.Structure):
                 ('nb', C.c_int32), ('reserved', C.c_int32)]
 
 
+class EnsembleConfig(C.Structure):
+    _fields_ = [('nchains', C.c_int64), ('nwalkers', C.c_int32), ('nfree', C.c_int32), ('nsteps', C.c_int64),
+                ('step0', C.c_int64), ('thin', C.c_int64), ('a', C.c_double), ('seed', C.c_uint64), ('chain0', C.c_int64)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     'gf_abi_version': (C.c_int, []),
@@ -92,6 +97,7 @@ _SIGNATURES = {
     'gf_scan_hist': (C.c_int, [C.POINTER(Model), C.POINTER(ScanConfig), _P, _P, _P]),
     'gf_scan_samples': (C.c_int, [C.POINTER(Model), C.POINTER(ScanConfig), _P, _P, _P, _P]),
     'gf_ternary_hist': (C.c_int, [_P, C.c_int64, C.c_int32, _P, _P]),
+    'gf_ensemble_run': (C.c_int, [C.POINTER(Model), C.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P]),
     'gf_selftest_math': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     'gf_fp64_peak_probe': (C.c_int, [C.c_int32, C.c_int64, _P, C.POINTER(C.c_double), _P]),
 }
@@ -114,7 +120,7 @@ def load():
             fn.restype, fn.argtypes = res, args
         if lib.gf_abi_version() != 1:
             raise GolemFlavorError('golemflavor_b200: ABI version mismatch, rebuild the library')
-        for which, struct in enumerate((Model, ScanConfig, PriorDim)):
+        for which, struct in enumerate((Model, ScanConfig, PriorDim, EnsembleConfig)):
             if lib.gf_sizeof(which) != C.sizeof(struct):
                 raise GolemFlavorError('golemflavor_b200: layout of {0} differs between _lib.py ({1} B) and the '
                                        'library ({2} B)'.format(struct.__name__, C.sizeof(struct), lib.gf_sizeof(which)))

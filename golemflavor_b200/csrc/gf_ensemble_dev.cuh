@@ -1,0 +1,81 @@
+/*
+ * gf_ensemble_dev.cuh -- one stretch-move update of the device-resident ensemble sampler
+ * (see gf_ensemble.cu and gf_ensemble_config in the C header for the RNG / proposal convention).
+ */
+#ifndef GF_ENSEMBLE_DEV_CUH
+#define GF_ENSEMBLE_DEV_CUH
+
+#include "gf_scan_dev.cuh"
+
+/* round-to-nearest operations that the compiler must not contract into FMAs, and L2 loads */
+#ifdef __CUDA_ARCH__
+#define GF_ADD_RN(a, b) __dadd_rn(a, b)
+#define GF_SUB_RN(a, b) __dsub_rn(a, b)
+#define GF_MUL_RN(a, b) __dmul_rn(a, b)
+#define GF_DIV_RN(a, b) __ddiv_rn(a, b)
+#define GF_LDCG(p) __ldcg(p)
+#else /* host instantiation (tests/host_harness, built with -ffp-contract=off) */
+#define GF_ADD_RN(a, b) ((a) + (b))
+#define GF_SUB_RN(a, b) ((a) - (b))
+#define GF_MUL_RN(a, b) ((a) * (b))
+#define GF_DIV_RN(a, b) ((a) / (b))
+#define GF_LDCG(p) (*(p))
+#endif
+
+struct gf_ens_args {
+    int64_t nchains, nsteps, step0, thin, chain0;
+    int32_t nwalkers, nfree;
+    double a;
+    uint64_t seed;
+    double* pos;
+    double* lnp;
+    double* chain;
+    double* lnp_chain;
+    unsigned long long* naccept;
+};
+
+/* one stretch-move update of walker k (in half h) of chain c */
+GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int h, int64_t step) {
+    const int ndim = m.ndim, half = A.nwalkers / 2;
+    const uint64_t gid = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)k;
+    const uint64_t s = (uint64_t)step;
+    const gf_u4 r = gf_philox4x32_10((uint32_t)gid, (uint32_t)s, (uint32_t)(s >> 32), 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+    /* no FMA contraction in the proposal: bit-reproducible with NumPy */
+    const double t = GF_ADD_RN(GF_MUL_RN(A.a - 1.0, gf_u01(r.x)), 1.0);
+    const double z = GF_DIV_RN(GF_MUL_RN(t, t), A.a);
+    int j = (int)(gf_u01(r.y) * (double)half);
+    j = j < half ? j : half - 1;
+    const double* p = A.pos + (c * A.nwalkers + k) * ndim;
+    const double* cj = A.pos + (c * A.nwalkers + (1 - h) * half + j) * ndim;
+    double q[GF_MAX_DIM];
+    /* positions of other walkers were written by other SMs before the last grid barrier: read them
+     * through L2 (ld.global.cg), not through this SM's non-coherent L1 */
+    for (int d = 0; d < ndim; ++d) {
+        const double cd = GF_LDCG(cj + d);
+        q[d] = GF_SUB_RN(cd, GF_MUL_RN(z, GF_SUB_RN(cd, GF_LDCG(p + d))));
+    }
+    double fr[3];
+    unsigned st = 0u;
+    const double lnew = gf_point_lnprob(m, [&](int d) { return q[d]; }, fr, st);
+    const double lold = GF_LDCG(A.lnp + c * A.nwalkers + k);
+    const double diff = (double)(A.nfree - 1) * log(z) + lnew - lold;
+    const bool accept = diff > log(gf_u01(r.z)); /* false for NaN */
+    if (accept) {
+        double* pw = A.pos + (c * A.nwalkers + k) * ndim;
+        for (int d = 0; d < ndim; ++d) pw[d] = q[d];
+        A.lnp[c * A.nwalkers + k] = lnew;
+    }
+    return accept ? 1u : 0u;
+}
+
+GF_HD void gf_ens_store(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int64_t slot, int64_t nstore) {
+    const int ndim = m.ndim;
+    const double* p = A.pos + (c * A.nwalkers + k) * ndim;
+    if (A.chain) {
+        double* o = A.chain + ((c * A.nwalkers + k) * nstore + slot) * ndim;
+        for (int d = 0; d < ndim; ++d) o[d] = p[d];
+    }
+    if (A.lnp_chain) A.lnp_chain[(c * A.nwalkers + k) * nstore + slot] = A.lnp[c * A.nwalkers + k];
+}
+
+#endif /* GF_ENSEMBLE_DEV_CUH */

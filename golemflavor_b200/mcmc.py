@@ -15,7 +15,7 @@ import sys
 
 import numpy as np
 
-__all__ = ['EnsembleSampler', 'mcmc', 'flat_seed', 'gaussian_seed', 'save_chains', 'integrated_time']
+__all__ = ['EnsembleSampler', 'DeviceEnsembleSampler', 'mcmc', 'flat_seed', 'gaussian_seed', 'save_chains', 'integrated_time']
 
 
 def _progress(iterable, total):
@@ -162,9 +162,143 @@ class EnsembleSampler(object):
         return results
 
 
-def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=True, seed=None):
+class DeviceEnsembleSampler(object):
+    """Device-resident stretch-move sampler (C ABI ``gf_ensemble_run``): proposal, log-posterior and
+    accept/reject of every half-step run inside one kernel, for ``nchains`` independent ensembles at
+    once; the whole ``run_mcmc`` call is a single cooperative launch when the batch is co-resident.
+
+    Same emcee-2 surface as ``EnsembleSampler`` (``chain``, ``lnprobability``, ``acceptance_fraction``,
+    ``acor``, ``flatchain``, ``reset``, ``run_mcmc``, ``sample``); with ``nchains > 1`` the arrays gain
+    a leading chain axis.  ``lnprob`` must be an ``llh.LnProb`` (the flattened model).  Columns that are
+    identical in all walkers of a chain stay frozen; pass ``nfree`` = number of sampled dimensions.
+    """
+
+    def __init__(self, nwalkers, ndim, lnprob, nchains=1, a=2.0, seed=0, nfree=None, store_lnprob=True, chain0=0):
+        from . import _lib
+        if nwalkers % 2 != 0:
+            raise ValueError('The number of walkers must be even.')
+        if not hasattr(lnprob, 'model') or lnprob.ndim != ndim:
+            raise ValueError('DeviceEnsembleSampler needs an llh.LnProb with ndim = {0}'.format(ndim))
+        self._lib = _lib
+        self.k, self.dim, self.a, self.nchains = int(nwalkers), int(ndim), float(a), int(nchains)
+        self.nfree = int(nfree) if nfree is not None else int(ndim)
+        if self.k < 2 * self.nfree:
+            raise ValueError('The number of walkers needs to be more than twice the dimension of your parameter space.')
+        self.lnprob, self.seed, self.store_lnprob, self.chain0 = lnprob, int(seed), bool(store_lnprob), int(chain0)
+        self.total_steps = 0   # global step counter = RNG counter offset: continuing a run never reuses draws
+        self.reset()
+
+    def reset(self):
+        self._chains, self._lnps = [], []
+        self._naccept = None
+        self.iterations = 0
+        self._last = None
+
+    def _cat(self, parts, tail):
+        import torch
+        if not parts:
+            return np.empty((self.nchains, self.k, 0) + tail)
+        return torch.cat(parts, dim=2).cpu().numpy()
+
+    def _squeeze(self, arr):
+        return arr[0] if self.nchains == 1 else arr
+
+    chain = property(lambda self: self._squeeze(self._cat(self._chains, (self.dim,))))
+    lnprobability = property(lambda self: self._squeeze(self._cat(self._lnps, ())))
+    flatchain = property(lambda self: self.chain.reshape((-1, self.dim)) if self.nchains == 1
+                         else self.chain.reshape((self.nchains, -1, self.dim)))
+
+    @property
+    def acceptance_fraction(self):
+        if self._naccept is None:
+            return self._squeeze(np.zeros((self.nchains, self.k)))
+        return self._squeeze(self._naccept.cpu().numpy().astype(np.float64) / max(self.iterations, 1))
+
+    @property
+    def acor(self):
+        return self.get_autocorr_time()
+
+    def get_autocorr_time(self, c=5.0):
+        ch = self._cat(self._chains, (self.dim,))
+        if ch.shape[2] < 50:
+            raise RuntimeError('The chain is too short to reliably estimate the autocorrelation time')
+        tau = np.array([integrated_time(np.swapaxes(x, 0, 1), c=c) for x in ch])
+        return self._squeeze(tau)
+
+    def run_mcmc(self, pos0, N, lnprob0=None, thin=1, store=True, return_tensor=False):
+        """Advance all chains by N steps.  pos0 [nwalkers, ndim] or [nchains, nwalkers, ndim]
+        (None: continue).  Returns (pos, lnprob, None) like emcee."""
+        import ctypes as C
+        _lib = self._lib
+        torch = _lib.torch_cuda()
+        if pos0 is None:
+            if self._last is None:
+                raise ValueError('Cannot have pos0=None if run_mcmc has never been called.')
+            pos, lnp = self._last
+        else:
+            pos = _lib.to_device(pos0, torch, self.dim).reshape(self.nchains, self.k, self.dim).clone()
+            lnp = None if lnprob0 is None else _lib.to_device(lnprob0, torch).reshape(self.nchains, self.k).clone()
+        if lnp is None:
+            lnp = self.lnprob.evaluate(pos.reshape(-1, self.dim)).reshape(self.nchains, self.k)
+        if bool(torch.isnan(lnp).any()):
+            raise ValueError('lnprob returned NaN.')
+        nstore = int(N) // int(thin) if store else 0
+        chain = torch.empty((self.nchains, self.k, nstore, self.dim), dtype=torch.float64, device='cuda') if nstore else None
+        lchain = torch.empty((self.nchains, self.k, nstore), dtype=torch.float64, device='cuda') \
+            if nstore and self.store_lnprob else None
+        if self._naccept is None:
+            self._naccept = torch.zeros((self.nchains, self.k), dtype=torch.int64, device='cuda')
+        cfg = _lib.EnsembleConfig(nchains=self.nchains, nwalkers=self.k, nfree=self.nfree, nsteps=int(N),
+                                  step0=self.total_steps, thin=int(thin), a=self.a, seed=self.seed, chain0=self.chain0)
+        _lib.check(_lib.load().gf_ensemble_run(self.lnprob.model.ref, C.byref(cfg), _lib.ptr(pos), _lib.ptr(lnp),
+                                               _lib.ptr(chain), _lib.ptr(lchain), _lib.ptr(self._naccept),
+                                               _lib.stream_ptr(torch)))
+        self.total_steps += int(N)
+        self.iterations += int(N)
+        if chain is not None:
+            self._chains.append(chain)
+        if lchain is not None:
+            self._lnps.append(lchain)
+        self._last = (pos, lnp)
+        if return_tensor:
+            return pos, lnp, None
+        return self._squeeze(pos.cpu().numpy()), self._squeeze(lnp.cpu().numpy()), None
+
+    def sample(self, p0, lnprob0=None, rstate0=None, iterations=1, thin=1, storechain=True):
+        """emcee-2 generator interface (``mcmc.py:34-41``).  The device sampler advances all
+        ``iterations`` in one launch and yields once."""
+        yield self.run_mcmc(p0, iterations, lnprob0=lnprob0, thin=thin, store=storechain)
+
+
+def _as_lnprob_object(ln_prob):
+    """``LnProb`` behind ``ln_prob`` if it is one, or a ``functools.partial`` of ``llh.ln_prob``
+    with its three closure arguments bound (the reference's calling pattern, ``scripts/fr.py:182-187``)."""
+    from . import llh
+    if isinstance(ln_prob, llh.LnProb):
+        return ln_prob
+    func = getattr(ln_prob, 'func', None)
+    if func is llh.ln_prob:
+        kw = dict(ln_prob.keywords or {})
+        names = ['args', 'asimov_paramset', 'llh_paramset']
+        pos = list(ln_prob.args or ())
+        try:
+            bound = [kw[n] if n in kw else pos.pop(0) for n in names]
+        except IndexError:
+            return None
+        return llh.LnProb(*bound)
+    return None
+
+
+def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=True, seed=None, device=None):
     """Run burn-in, reset, run, flatten walker-major (``mcmc.py:27-53``).  Returns ``samples[nwalkers*nsteps, ndim]``."""
-    sampler = EnsembleSampler(nwalkers, ndim, ln_prob, threads=threads, vectorize=vectorize, seed=seed)
+    fn = _as_lnprob_object(ln_prob) if device in (None, True) else None
+    if device is True and fn is None:
+        raise ValueError('device=True needs an llh.LnProb or a partial of llh.ln_prob')
+    if fn is not None:
+        # device-resident sampler: proposal + log-posterior + accept in one kernel, no host loop
+        sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, seed=0 if seed is None else seed)
+    else:
+        sampler = EnsembleSampler(nwalkers, ndim, ln_prob, threads=threads, vectorize=vectorize, seed=seed)
     print("Running burn-in")
     pos = np.asarray(p0)
     for pos, _, _ in _progress(sampler.sample(p0, iterations=burnin), burnin):

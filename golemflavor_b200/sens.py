@@ -1,0 +1,93 @@
+"""Sensitivity sweep over (operator dimension, new-physics scale) grid points
+(``scripts/sens.py:184-314``: one HTCondor job per (dimension, Lambda-segment), ``submitter/sens_dag.py:76-95``).
+
+The reference fixes the scale parameter at each grid value (``sens.py:261-266``: ``scale_prm.value = scale``
+and the sampler runs over all *non-SCALE* params) and runs MultiNest with the proprietary GolemFit
+likelihood.  Here every grid point is an independent emcee-style chain of the Gaussian flavor-ratio
+posterior with log10(Lambda) FROZEN at the grid value: all chains of one dimension run in ONE launch of
+the device-resident ensemble sampler (``gf_ensemble_run``), grid points are sharded over the ranks of
+the process group with no communication during sampling, and only the per-point summaries are
+gathered at the end (``all_gather`` of a few numbers per chain).
+"""
+
+from argparse import Namespace
+
+import numpy as np
+
+from . import _lib, llh
+from . import model as _model
+from .enums import ParamTag, Texture
+from .mcmc import DeviceEnsembleSampler, flat_seed
+from .param import Param, ParamSet
+from .scan import DEFAULT_BINNING, _dist, shard_range, sm_paramset
+
+__all__ = ['scale_grid', 'sweep_paramset', 'sweep']
+
+
+def scale_grid(dimension, segments):
+    """``eval_scales``: the null point -100 followed by ``segments - 1`` equidistant values inside
+    ``SCALE_BOUNDARIES[dimension]`` (``sens.py:199-201``)."""
+    lo, hi = _model.SCALE_BOUNDARIES[int(dimension)]
+    return np.concatenate([[-100.0], np.linspace(lo, hi, int(segments) - 1)])
+
+
+def sweep_paramset(dimension):
+    """6 SM nuisance params + logLam; the logLam box is widened to include the null point -100."""
+    b = _model.SCALE_BOUNDARIES[int(dimension)]
+    return ParamSet(sm_paramset(with_mass=True) + [
+        Param(name='logLam', value=float(np.mean(b)), ranges=[-101.0, float(b[1])], std=3, tag=ParamTag.SCALE)])
+
+
+def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, source_ratio=(1, 2, 0),
+          injected_ratio=(1, 1, 1), smearing=0.02, nwalkers=60, burnin=200, nsteps=1000, seed=25,
+          binning=DEFAULT_BINNING, distributed=True):
+    """Run one chain per (dimension, scale) grid point.
+
+    Returns a dict of arrays over all grid points (identical on every rank):
+    ``dimension``, ``scale``, ``mean_lnprob`` (posterior mean of ln_prob), ``max_lnprob``,
+    ``acceptance`` (mean acceptance fraction), ``mean_fr`` [n, 3] (posterior-mean measured composition).
+    """
+    torch = _lib.torch_cuda()
+    dist = _dist() if distributed else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    grid = [(int(d), float(s)) for d in dimensions for s in scale_grid(d, segments)]
+    start, count = shard_range(len(grid), rank, world)
+    mine = grid[start:start + count]
+    rows = torch.zeros((len(grid), 8), dtype=torch.float64, device='cuda')
+    src = np.asarray(source_ratio, dtype=np.float64)
+    inj = np.asarray(injected_ratio, dtype=np.float64)
+    rng = np.random.RandomState(seed)
+    for dim in sorted({d for d, _ in mine}):
+        idx = [start + i for i, (d, _) in enumerate(mine) if d == dim]
+        scales = np.array([grid[i][1] for i in idx])
+        pset = sweep_paramset(dim)
+        args = Namespace(source_ratio=src / src.sum(), dimension=dim, texture=texture, binning=np.asarray(binning),
+                         no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing))
+        fn = llh.LnProb(args, None, pset)
+        nchains, ndim = len(idx), len(pset)
+        state = np.random.get_state()
+        np.random.seed(rng.randint(2 ** 31 - 1))
+        p0 = np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)])
+        np.random.set_state(state)
+        p0[:, :, ndim - 1] = scales[:, None]                      # frozen column: identical in all walkers
+        sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, nchains=nchains, seed=seed + 1000 * dim, nfree=ndim - 1,
+                                        chain0=idx[0])
+        sampler.run_mcmc(p0, burnin, store=False)
+        sampler.reset()
+        pos, lnp, _ = sampler.run_mcmc(None, nsteps, store=False, return_tensor=True)
+        # summaries from the final ensemble + the acceptance counters (no chain leaves the device)
+        _, fr, _ = fn.evaluate(pos.reshape(-1, ndim), want_fr=True, want_status=True)
+        fr = fr.reshape(nchains, nwalkers, 3)
+        acc = torch.as_tensor(np.atleast_2d(sampler.acceptance_fraction), device='cuda').reshape(nchains, nwalkers)
+        ii = torch.as_tensor(idx, device='cuda')
+        rows[ii, 0] = float(dim)
+        rows[ii, 1] = torch.as_tensor(scales, device='cuda')
+        rows[ii, 2] = lnp.mean(dim=1)
+        rows[ii, 3] = lnp.max(dim=1).values
+        rows[ii, 4] = acc.mean(dim=1)
+        rows[ii, 5:8] = fr.mean(dim=1)
+    if dist and world > 1:
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM)              # disjoint rows: sum == gather
+    out = rows.cpu().numpy()
+    return {'dimension': out[:, 0].astype(int), 'scale': out[:, 1], 'mean_lnprob': out[:, 2], 'max_lnprob': out[:, 3],
+            'acceptance': out[:, 4], 'mean_fr': out[:, 5:8]}

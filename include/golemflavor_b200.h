@@ -124,7 +124,7 @@ typedef struct gf_scan_config {
 
 /* ---- library ---------------------------------------------------------- */
 int gf_abi_version(void);
-/* sizeof(gf_model) / sizeof(gf_scan_config) / sizeof(gf_prior_dim) for which = 0 / 1 / 2: lets a
+/* sizeof(gf_model) / gf_scan_config / gf_prior_dim / gf_ensemble_config for which = 0 / 1 / 2 / 3: lets a
  * foreign-language binding verify its struct layout at load time. */
 uint64_t gf_sizeof(int32_t which);
 const char* gf_last_error(void);
@@ -193,6 +193,42 @@ int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_
                     double* d_fr /*[count][3] or NULL*/, uint8_t* d_status /*[count] or NULL*/, void* stream);
 /* Histogram of given compositions (bit-exact np.histogramdd), ADDS into d_hist. */
 int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsigned long long* d_hist, void* stream);
+
+/* ---- ensemble sampler --------------------------------------------------- */
+/*
+ * Device-resident affine-invariant ensemble sampler: the stretch move of emcee's EnsembleSampler
+ * (Goodman & Weare 2010; red/blue half-ensembles, parameter a) that golemflavor/mcmc.py:27-53 drives
+ * from Python, for `nchains` INDEPENDENT ensembles of `nwalkers` walkers at once (one thread per
+ * walker pair; the whole run is one cooperative launch with a grid barrier per half-step when the
+ * batch is co-resident, one launch per half-step otherwise).
+ *
+ * Randomness (reproducible on the CPU, see tests): walker k of chain c at global step s uses
+ * Philox4x32-10 with key = (lo32(seed), hi32(seed)), counter = ((chain0 + c)*nwalkers + k, lo32(s), hi32(s), 0)
+ * (chain0 = global index of this call's first chain, so that a set of chains gives the same result
+ * however it is sharded over calls or GPUs):
+ *   word 0 -> z = ((a-1) u + 1)^2 / a,  word 1 -> partner j = floor(u * nwalkers/2) in the other half,
+ *   word 2 -> accept iff (nfree-1) ln z + lnp(q) - lnp(p) > ln u;   u = (word + 0.5) 2^-32,
+ *   proposal q = c_j - z (c_j - p_k), evaluated without FMA contraction.
+ * Columns whose value is identical in all walkers of a chain stay frozen (q = c - z*0); `nfree` is
+ * the number of sampled dimensions that enters the acceptance factor.
+ */
+typedef struct gf_ensemble_config {
+    int64_t nchains;     /* independent ensembles                                   */
+    int32_t nwalkers;    /* walkers per ensemble (even, >= 2)                       */
+    int32_t nfree;       /* dimensions that actually move (<= model.ndim)           */
+    int64_t nsteps;      /* steps to advance                                        */
+    int64_t step0;       /* global index of the first step (RNG counter offset)     */
+    int64_t thin;        /* store every thin-th step                                */
+    double a;            /* stretch scale (emcee default 2.0)                       */
+    uint64_t seed;
+    int64_t chain0;      /* global index of the first chain (RNG counter offset)    */
+} gf_ensemble_config;
+/* d_pos [nchains][nwalkers][ndim] and d_lnp [nchains][nwalkers] are updated in place (d_lnp must hold
+ * ln_prob(d_pos) on entry: call gf_lnprob first).  Optional outputs: d_chain
+ * [nchains][nwalkers][nsteps/thin][ndim] (emcee's `chain` layout, mcmc.py:44), d_lnp_chain
+ * [nchains][nwalkers][nsteps/thin], d_naccept [nchains][nwalkers] (ADDS accepted-move counts). */
+int gf_ensemble_run(const gf_model* model, const gf_ensemble_config* cfg, double* d_pos, double* d_lnp, double* d_chain,
+                    double* d_lnp_chain, unsigned long long* d_naccept, void* stream);
 
 /* ---- measurement helper ----------------------------------------------- */
 /* fp64 throughput microbenchmarks: `iters` dependent FMAs x 8 chains per thread on a full grid;

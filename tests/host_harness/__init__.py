@@ -87,3 +87,18 @@ def eig(ham):
     lam, vec, xf, ok = np.empty((n, 3)), np.empty((n, 18)), np.empty((n, 4)), np.empty(n, dtype=np.uint8)
     load().hh_eig(_p(hv), C.c_int64(n), _p(lam), _p(vec), _p(xf), _p(ok))
     return lam, vec.view(np.complex128).reshape(n, 3, 3), xf.reshape(n, 2, 2), ok.astype(bool)
+
+
+def ensemble(fm, pos, lnp, nsteps, nwalkers, nchains=1, nfree=None, step0=0, thin=1, a=2.0, seed=0, chain0=0):
+    """Sequential host replay of gf_ensemble_run.  Returns (pos, lnp, chain, lnp_chain, naccept)."""
+    ndim = fm.ndim
+    pos = np.array(pos, dtype=np.float64).reshape(nchains, nwalkers, ndim).copy()
+    lnp = np.array(lnp, dtype=np.float64).reshape(nchains, nwalkers).copy()
+    nstore = nsteps // thin
+    chain = np.zeros((nchains, nwalkers, nstore, ndim))
+    lchain = np.zeros((nchains, nwalkers, nstore))
+    nacc = np.zeros((nchains, nwalkers), dtype=np.uint64)
+    cfg = _lib.EnsembleConfig(nchains=nchains, nwalkers=nwalkers, nfree=nfree or ndim, nsteps=nsteps, step0=step0,
+                              thin=thin, a=a, seed=seed, chain0=chain0)
+    _lib.check(load().hh_ensemble(fm.ref, C.byref(cfg), _p(pos), _p(lnp), _p(chain), _p(lchain), _p(nacc)))
+    return pos, lnp, chain, lchain, nacc.astype(np.int64)

@@ -13,7 +13,7 @@
 #include <string.h>
 
 #include "../../golemflavor_b200/csrc/gf_common.cuh"
-#include "../../golemflavor_b200/csrc/gf_scan_dev.cuh"
+#include "../../golemflavor_b200/csrc/gf_ensemble_dev.cuh"
 
 extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st) {
     gf_dev_model d;
@@ -84,4 +84,32 @@ extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, do
         fast_ok[i] = gfp_herm3_x4_fast(wpoly, m, x) ? 1 : 0;
         x_fast[4 * i] = x.x00; x_fast[4 * i + 1] = x.x01; x_fast[4 * i + 2] = x.x10; x_fast[4 * i + 3] = x.x11;
     }
+}
+
+/* sequential replay of gf_ensemble_run: same update function, same order of half-steps */
+extern "C" int hh_ensemble(const gf_model* model, const gf_ensemble_config* cfg, double* pos, double* lnp, double* chain,
+                           double* lnp_chain, unsigned long long* naccept) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    gf_ens_args A;
+    A.nchains = cfg->nchains; A.nsteps = cfg->nsteps; A.step0 = cfg->step0; A.thin = cfg->thin;
+    A.nwalkers = cfg->nwalkers; A.nfree = cfg->nfree; A.a = cfg->a; A.seed = cfg->seed; A.chain0 = cfg->chain0;
+    A.pos = pos; A.lnp = lnp; A.chain = chain; A.lnp_chain = lnp_chain; A.naccept = naccept;
+    const int half = cfg->nwalkers / 2;
+    const int64_t nstore = cfg->nsteps / cfg->thin;
+    for (int64_t s = 0; s < cfg->nsteps; ++s) {
+        for (int h = 0; h < 2; ++h) {
+            /* the whole half proposes from the state BEFORE any walker of that half moved: partners
+             * come from the other half, so updating in place is equivalent */
+            for (int64_t c = 0; c < cfg->nchains; ++c)
+                for (int w = 0; w < half; ++w) {
+                    const unsigned acc = gf_ens_update(d, A, c, h * half + w, h, cfg->step0 + s);
+                    if (naccept) naccept[c * cfg->nwalkers + h * half + w] += acc;
+                }
+        }
+        if ((s + 1) % cfg->thin == 0 && (s + 1) / cfg->thin <= nstore)
+            for (int64_t c = 0; c < cfg->nchains; ++c)
+                for (int k = 0; k < cfg->nwalkers; ++k) gf_ens_store(d, A, c, k, (s + 1) / cfg->thin - 1, nstore);
+    }
+    return 0;
 }

@@ -440,3 +440,90 @@ def test_emcee_driver_on_gpu_lnprob(torch, golden, capsys):
     measured = fr.u_to_fr(fr.angles_to_fr(samples[:, 4:6]), fr.angles_to_u(samples[:, :4]))
     bf = np.array(go.angles_to_fr(g['asimov_angles']))
     assert np.abs(np.median(measured, axis=0) - bf).max() < 0.03
+
+
+# ------------------------------------------------------------------ device-resident ensemble sampler
+def test_device_sampler_replays_numpy_stretch_move(torch, golden):
+    """gf_ensemble_run against the NumPy stretch-move restatement, both scoring proposals with the
+    CUDA log-posterior: identical chains (the acceptance test can only differ on a measure-zero tie)."""
+    import ref_sampler
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(0)
+    k = 64
+    p0 = models.draw_in_ranges(pset, k, rng, seeds=True)
+    p0[:, 4], p0[:, 5] = rng.uniform(.9, 1, k), rng.uniform(.8, 1, k)
+    l0 = fn(p0)
+    s = mcmc.DeviceEnsembleSampler(k, 6, fn, seed=5)
+    lib = _lib.load()
+    before = lib.gf_launch_count()
+    pos, lnp, _ = s.run_mcmc(p0, 120)
+    assert lib.gf_launch_count() - before == 2           # initial scoring + ONE cooperative launch
+    rp, rl, rchain, racc = ref_sampler.run(lambda q: fn(q), p0, l0, 120, seed=5)
+    same = np.mean(s.chain == rchain)
+    assert same > 0.999, same
+    assert s.chain.shape == (k, 120, 6) and s.lnprobability.shape == (k, 120)
+    assert np.array_equal(s.lnprobability[:, -1], lnp)
+    assert np.allclose(s.acceptance_fraction, racc / 120.0) and 0.2 < s.acceptance_fraction.mean() < 0.7
+    # continue: pos0=None picks up where the run stopped, with fresh randomness
+    s.run_mcmc(None, 30)
+    _, _, rchain2, _ = ref_sampler.run(lambda q: fn(q), rp, rl, 30, seed=5, step0=120)
+    assert np.mean(s.chain[:, 120:] == rchain2) > 0.999 and s.chain.shape[1] == 150
+
+
+def test_device_sampler_many_chains_and_launch_paths(torch, golden):
+    """Batched independent chains: a co-resident batch (one cooperative launch) and a batch too large
+    for co-residency (one launch per half-step) must give the same chains."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(2)
+    k, nchains, nsteps = 32, 6000, 6
+    p0 = models.draw_in_ranges(pset, k * nchains, rng, seeds=True).reshape(nchains, k, 6)
+    p0[:, :, 4], p0[:, :, 5] = rng.uniform(.9, 1, (nchains, k)), rng.uniform(.8, 1, (nchains, k))
+    lib = _lib.load()
+    big = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3)
+    before = lib.gf_launch_count()
+    big.run_mcmc(p0, nsteps)
+    assert lib.gf_launch_count() - before == 1 + 3 * nsteps     # scoring + (2 half-steps + 1 store) per step
+    sub = slice(4100, 4110)
+    small = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=10, seed=3, chain0=4100)
+    small.run_mcmc(p0[sub], nsteps)
+    assert np.array_equal(big.chain[sub], small.chain)
+    assert big.chain.shape == (nchains, k, nsteps, 6) and big.acceptance_fraction.shape == (nchains, k)
+
+
+def test_mcmc_driver_uses_device_sampler_and_recovers_injection(torch, golden, capsys):
+    """mcmc.mcmc with a partial of llh.ln_prob (the reference's calling pattern, scripts/fr.py:182-187)
+    runs on the device-resident sampler; the BSM posterior sampled with logLam free stays inside the
+    prior box and prefers compositions near the injected one."""
+    from functools import partial
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    ln_prob = partial(llh.ln_prob, args=args, asimov_paramset=asimov, llh_paramset=pset)
+    np.random.seed(25)
+    k = 256
+    p0 = mcmc.flat_seed(pset, k)
+    p0[:, 4], p0[:, 5] = np.random.uniform(0.9, 1.0, k), np.random.uniform(0.8, 1.0, k)
+    samples = mcmc.mcmc(p0, ln_prob, 6, k, burnin=400, nsteps=400, seed=4)
+    assert isinstance(mcmc.mcmc.last_sampler, mcmc.DeviceEnsembleSampler)
+    assert samples.shape == (k * 400, 6)
+    lo, hi = np.array(pset.ranges).T
+    assert np.all(samples >= lo) and np.all(samples <= hi)
+    measured = fr.u_to_fr(fr.angles_to_fr(samples[:, 4:6]), fr.angles_to_u(samples[:, :4]))
+    bf = np.array(go.angles_to_fr(g['asimov_angles']))
+    assert np.abs(np.median(measured, axis=0) - bf).max() < 0.03
+    assert 0.15 < mcmc.mcmc.last_sampler.acceptance_fraction.mean() < 0.7
+
+
+def test_sens_sweep_small(torch):
+    from golemflavor_b200 import sens
+    out = sens.sweep(dimensions=(3, 6), segments=5, nwalkers=32, burnin=60, nsteps=60, injected_ratio=(1, 1, 1), distributed=False)
+    assert len(out['scale']) == 10 and set(out['dimension']) == {3, 6}
+    assert np.all(out['scale'][out['dimension'] == 3] == sens.scale_grid(3, 5))
+    assert np.all(np.isfinite(out['mean_lnprob'])) and np.all((out['acceptance'] > 0.02) & (out['acceptance'] < 0.9))
+    assert np.abs(out['mean_fr'].sum(axis=1) - 1).max() < 1e-12
+    # the null point (logLam = -100: no new physics) and the smallest in-range scale agree; the largest scale differs
+    d6 = out['dimension'] == 6
+    assert np.abs(out['mean_fr'][d6][0] - out['mean_fr'][d6][1]).max() < 0.05

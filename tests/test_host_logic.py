@@ -295,3 +295,61 @@ def test_harness_histogram_is_bit_exact_np_histogramdd():
     fr[900:905] = [[1, 0, 0], [0, 1, 0], [0, 0, 1], [1.0000000001, 0, 0], [np.nan, 0.5, 0.5]]
     for nb in (0, 1, 25, 125, 200):
         assert np.array_equal(hh.hist(fr, nb), go.ternary_histogram(fr, nb)), nb
+
+
+# ------------------------------------------------------------------ ensemble sampler update on the host harness
+def test_harness_ensemble_update_is_the_numpy_stretch_move(golden):
+    """The kernel's per-walker update (RNG convention, proposal, acceptance rule, in-place half-step
+    semantics), replayed on the host, must reproduce an independent NumPy stretch-move sampler
+    bit-for-bit when both score proposals with the same log-posterior."""
+    import ref_sampler
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    rng = np.random.default_rng(0)
+    k = 32
+    p0 = models.draw_in_ranges(pset, k, rng, seeds=True)
+    p0[:, 4], p0[:, 5] = rng.uniform(.9, 1, k), rng.uniform(.8, 1, k)
+    l0 = hh.lnprob(fm, p0)[0]
+    pos, lnp, chain, lch, nacc = hh.ensemble(fm, p0, l0, 150, k, seed=5)
+    rp, rl, rchain, racc = ref_sampler.run(lambda q: hh.lnprob(fm, q)[0], p0, l0, 150, seed=5)
+    assert np.array_equal(chain[0], rchain) and np.array_equal(nacc[0], racc) and np.array_equal(lnp[0], rl)
+    assert 0.2 < nacc.mean() / 150 < 0.7
+    assert np.array_equal(lch[0][:, -1], lnp[0])
+    # continuing with step0 = 150 equals one 300-step run; thinning stores every other step
+    pos2, lnp2, chain2, _, _ = hh.ensemble(fm, pos, lnp, 150, k, seed=5, step0=150)
+    _, _, chain_all, _, _ = hh.ensemble(fm, p0, l0, 300, k, seed=5)
+    assert np.array_equal(chain_all[0][:, 150:], chain2[0])
+    _, _, thin, _, _ = hh.ensemble(fm, p0, l0, 300, k, seed=5, thin=2)
+    assert np.array_equal(thin[0], chain_all[0][:, 1::2])
+    # two chains in one call are independent and shard-invariant (chain0 offsets the RNG counter)
+    q0 = np.stack([p0, p0[::-1]])
+    lq = np.stack([l0, l0[::-1]])
+    _, _, both, _, _ = hh.ensemble(fm, q0, lq, 40, k, nchains=2, seed=9)
+    _, _, second, _, _ = hh.ensemble(fm, q0[1], lq[1], 40, k, nchains=1, seed=9, chain0=1)
+    assert np.array_equal(both[1], second[0]) and not np.array_equal(both[0], both[1])
+
+
+def test_harness_ensemble_frozen_column_and_posterior(golden):
+    """BSM model with log10(Lambda) frozen (the sens sweep): the frozen column never moves and the
+    free-dimension count enters the acceptance factor."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    np.random.seed(3)
+    k = 28
+    p0 = mcmc.flat_seed(pset, k)
+    p0[:, 6] = -40.0
+    l0 = hh.lnprob(fm, p0)[0]
+    pos, lnp, chain, _, nacc = hh.ensemble(fm, p0, l0, 60, k, nfree=6, seed=1)
+    assert np.all(chain[0][:, :, 6] == -40.0) and nacc.sum() > 0
+    assert np.allclose(hh.lnprob(fm, pos[0])[0], lnp[0], rtol=0, atol=0)
+    assert lnp.mean() > l0.mean()    # the ensemble climbs towards the posterior bulk
+
+
+def test_sens_grid_matches_reference_definition():
+    from golemflavor_b200 import sens
+    g = sens.scale_grid(6, 10)       # sens.py:199-201
+    assert g[0] == -100 and len(g) == 10 and np.allclose(g[1:], np.linspace(-56, -30, 9))
+    ps = sens.sweep_paramset(3)
+    assert ps.names[-1] == 'logLam' and ps['logLam'].ranges[0] < -100
