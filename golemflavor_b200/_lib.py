@@ -42,12 +42,12 @@ class Model(C.Structure):
         ('col_np', C.c_int32 * 4),
         ('col_scale', C.c_int32),
         ('col_x', C.c_int32),
+        ('col_src3', C.c_int32 * 3),
         ('no_bsm', C.c_int32),
         ('dimension', C.c_int32),
         ('nbins', C.c_int32),
         ('llh_kind', C.c_int32),
         ('emulate_underflow', C.c_int32),
-        ('reserved', C.c_int32),
         ('fixed_sm', C.c_double * 4),
         ('fixed_mass', C.c_double * 2),
         ('fixed_src', C.c_double * 3),

@@ -97,7 +97,8 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
     struct { const int32_t* src; int32_t* dst; int n; const char* name; } cols[] = {
         {m->col_sm, d->col_sm, 4, "col_sm"},       {m->col_mass, d->col_mass, 2, "col_mass"},
         {m->col_src, d->col_src, 2, "col_src"},    {m->col_np, d->col_np, 4, "col_np"},
-        {&m->col_scale, &d->col_scale, 1, "col_scale"}, {&m->col_x, &d->col_x, 1, "col_x"}};
+        {&m->col_scale, &d->col_scale, 1, "col_scale"}, {&m->col_x, &d->col_x, 1, "col_x"},
+        {m->col_src3, d->col_src3, 3, "col_src3"}};
     for (auto& c : cols)
         for (int k = 0; k < c.n; ++k) {
             GF_REQUIRE(c.src[k] >= -1 && c.src[k] < m->ndim, "model.%s[%d] = %d outside [-1, ndim)", c.name, k, c.src[k]);
@@ -105,6 +106,9 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
         }
     GF_REQUIRE((m->col_src[0] >= 0) == (m->col_src[1] >= 0), "model.col_src: both source angles must be sampled or neither");
     GF_REQUIRE(!(m->col_src[0] >= 0 && m->col_x >= 0), "model: col_src and col_x are mutually exclusive");
+    GF_REQUIRE((m->col_src3[0] >= 0) == (m->col_src3[1] >= 0) && (m->col_src3[0] >= 0) == (m->col_src3[2] >= 0),
+               "model.col_src3: all three source ratios must be sampled or none");
+    GF_REQUIRE(!(m->col_src3[0] >= 0 && (m->col_src[0] >= 0 || m->col_x >= 0)), "model: col_src3 excludes col_src and col_x");
     d->np_free = 0;
     for (int k = 0; k < 4; ++k) d->np_free |= (m->col_np[k] >= 0);
 
@@ -113,7 +117,7 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
     memcpy(d->fixed_src, m->fixed_src, sizeof(d->fixed_src));
     memcpy(d->fixed_np, m->fixed_np, sizeof(d->fixed_np));
     d->fixed_loglam = m->fixed_loglam;
-    if (m->col_src[0] < 0 && m->col_x < 0) {
+    if (m->col_src[0] < 0 && m->col_x < 0 && m->col_src3[0] < 0) {
         const double s = m->fixed_src[0] + m->fixed_src[1] + m->fixed_src[2];
         GF_REQUIRE(isfinite(s) && s != 0.0, "model.fixed_src sums to %g", s);
     }

@@ -15,7 +15,7 @@
 
 struct gf_dev_model {
     int32_t ndim, no_bsm, nbins, llh_kind, emulate_underflow, np_free;
-    int32_t col_sm[4], col_mass[2], col_src[2], col_np[4], col_scale, col_x;
+    int32_t col_sm[4], col_mass[2], col_src[2], col_np[4], col_scale, col_x, col_src3[3];
     double fixed_sm[4], fixed_mass[2], fixed_src[3], fixed_np[4], fixed_loglam;
     gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
     double wpoly[GFP_W_POLY_N]; /* cos(phi/3) polynomial, direct constant-bank operands  */
@@ -56,6 +56,10 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
     q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
+    } else if (m.col_src3[0] >= 0) {
+        q.src[0] = get(m.col_src3[0]);
+        q.src[1] = get(m.col_src3[1]);
+        q.src[2] = get(m.col_src3[2]);
     } else if (m.col_x >= 0) {
         const double x = get(m.col_x); /* scripts/mc_x.py:187: source = (x, 1-x, 0) */
         q.src[0] = x;

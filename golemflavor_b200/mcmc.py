@@ -186,13 +186,15 @@ class DeviceEnsembleSampler(object):
             raise ValueError('The number of walkers needs to be more than twice the dimension of your parameter space.')
         self.lnprob, self.seed, self.store_lnprob, self.chain0 = lnprob, int(seed), bool(store_lnprob), int(chain0)
         self.total_steps = 0   # global step counter = RNG counter offset: continuing a run never reuses draws
+        self._last = None
         self.reset()
 
     def reset(self):
+        """Forget the stored chain and the acceptance counters (``mcmc.py:36``); the current ensemble
+        stays on the device so that ``run_mcmc(None, n)`` continues from it."""
         self._chains, self._lnps = [], []
         self._naccept = None
         self.iterations = 0
-        self._last = None
 
     def _cat(self, parts, tail):
         import torch

@@ -65,7 +65,7 @@ class FlatModel(object):
 
 def _new_struct():
     m = _lib.Model()
-    for arr in (m.col_sm, m.col_mass, m.col_src, m.col_np):
+    for arr in (m.col_sm, m.col_mass, m.col_src, m.col_np, m.col_src3):
         for k in range(len(arr)):
             arr[k] = -1
     m.col_scale = m.col_x = -1
@@ -105,7 +105,9 @@ def flatten(args, asimov_paramset, llh_paramset, likelihood=None):
         if all six of ``s_12_2 c_13_4 s_23_2 dcp m21_2 m3x_2`` are present (``fr.py:425-435``),
         on the SM-only path when the four ``SM_ANGLES`` are present (``inference.ipynb`` cell 21);
         otherwise NuFIT values are used (``fr.py:42, 313``);
-      * ``SRCANGLES``-tagged params give the source composition, else ``args.source_ratio``;
+      * ``SRCANGLES``-tagged params give the source composition -- two: the angles (sin^4 phi, cos 2psi) of
+        ``fr.angles_to_fr``; one: x with source (x, 1-x, 0) (``mc_x.py:187``); three: raw ratios normalised
+        by ``u_to_fr`` -- else ``args.source_ratio``;
       * a ``SCALE``-tagged param switches on the binned BSM path (``fr.py:421-423``); with
         ``Texture.NONE`` the four ``MMANGLES`` params are the new-physics mixing angles, with a
         fixed texture they come from ``fr.py:370-376``;
@@ -129,9 +131,11 @@ def flatten(args, asimov_paramset, llh_paramset, likelihood=None):
 
     if len(src_cols) == 1:
         m.col_x = src_cols[0]  # scripts/mc_x.py:187: a single SRCANGLES param x, source = (x, 1-x, 0)
+    elif len(src_cols) == 3:
+        m.col_src3[:] = src_cols  # three raw source ratios, normalised by u_to_fr (fr.py:535)
     elif src_cols:
         if len(src_cols) != 2:
-            raise ValueError('expected one or two SRCANGLES params, got {0}'.format(len(src_cols)))
+            raise ValueError('expected one, two or three SRCANGLES params, got {0}'.format(len(src_cols)))
         m.col_src[:] = src_cols
     else:
         m.fixed_src[:] = [float(x) for x in args.source_ratio]

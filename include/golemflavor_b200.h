@@ -80,12 +80,13 @@ typedef struct gf_model {
     int32_t col_np[4];    /* theta columns of the MMANGLES (NP mixing);   -1 = fixed_np   */
     int32_t col_scale;    /* theta column of logLam (SCALE tag); -1 = fixed_loglam        */
     int32_t col_x;        /* theta column of x, source = (x, 1-x, 0) (scripts/mc_x.py:187); -1 = unused */
+    int32_t col_src3[3];  /* theta columns of three raw source ratios (normalised by u_to_fr, fr.py:535;
+                             BASELINE config 1: "3 source-flavor params, fixed PMNS"); -1 = unused */
     int32_t no_bsm;       /* 1: skip the BSM path, fr = u_to_fr(source, sm_u) (notebook SM model) */
     int32_t dimension;    /* args.dimension (3..8)                                         */
     int32_t nbins;        /* len(args.binning) - 1                                         */
     int32_t llh_kind;     /* GF_LLH_*                                                      */
     int32_t emulate_underflow; /* 1: multi_gaussian returns -inf where the reference's pdf underflows */
-    int32_t reserved;
     double fixed_sm[4];   /* default NUFIT angles (fr.py:313)                              */
     double fixed_mass[2]; /* default MASS_EIGENVALUES (fr.py:42)                           */
     double fixed_src[3];  /* args.source_ratio (need not be normalised)                    */

@@ -64,3 +64,15 @@ def bsm_model_c3(asimov_angles, dim=6, texture=Texture.OET, source=(1, 2, 0), sm
 def draw_in_ranges(pset, n, rng, seeds=False):
     box = np.array(pset.seeds if seeds else pset.ranges, dtype=np.float64)
     return rng.uniform(box[:, 0], box[:, 1], size=(n, len(pset)))
+
+
+def sm_fit_c1(asimov_angles, smearing=0.02):
+    """BASELINE config 1: 3 source-flavor params (raw ratios in [0, 1]), fixed NuFIT PMNS, Gaussian LLH."""
+    tag = ParamTag.BESTFIT
+    asimov = ParamSet([
+        Param(name='measured_angle1', value=float(asimov_angles[0]), ranges=[0., 1.], std=smearing, tag=tag),
+        Param(name='measured_angle2', value=float(asimov_angles[1]), ranges=[-1., 1.], std=smearing, tag=tag)])
+    tag = ParamTag.SRCANGLES
+    eps = 1e-6
+    src = [Param(name='f_%s' % n, value=1. / 3, ranges=[eps, 1.], tag=tag) for n in ('e', 'mu', 'tau')]
+    return Namespace(source_ratio=[1, 2, 0], no_bsm=True), asimov, ParamSet(src)

@@ -431,11 +431,12 @@ def test_emcee_driver_on_gpu_lnprob(torch, golden, capsys):
     p0[:, 5] = np.random.uniform(0.8, 1.0, nwalkers)
     lib = _lib.load()
     before = lib.gf_launch_count()
-    samples = mcmc.mcmc(p0, fn, 6, nwalkers, burnin=300, nsteps=300, seed=2)
+    samples = mcmc.mcmc(p0, fn, 6, nwalkers, burnin=300, nsteps=300, seed=2, device=False)   # host-loop sampler
     launches = lib.gf_launch_count() - before
     assert samples.shape == (nwalkers * 300, 6)
     assert launches == 2 * 600 + 2               # two half-ensembles per step + two initial full scores
     sampler = mcmc.mcmc.last_sampler
+    assert isinstance(sampler, mcmc.EnsembleSampler)
     assert 0.1 < sampler.acceptance_fraction.mean() < 0.8
     measured = fr.u_to_fr(fr.angles_to_fr(samples[:, 4:6]), fr.angles_to_u(samples[:, :4]))
     bf = np.array(go.angles_to_fr(g['asimov_angles']))

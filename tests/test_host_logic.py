@@ -353,3 +353,21 @@ def test_sens_grid_matches_reference_definition():
     assert g[0] == -100 and len(g) == 10 and np.allclose(g[1:], np.linspace(-56, -30, 9))
     ps = sens.sweep_paramset(3)
     assert ps.names[-1] == 'logLam' and ps['logLam'].ranges[0] < -100
+
+
+def test_harness_config1_three_source_ratios_fixed_pmns(golden):
+    """BASELINE config 1 (the CPU-runnable case): 3 raw source ratios, fixed NuFIT PMNS."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.sm_fit_c1(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    assert list(fm.struct.col_src3) == [0, 1, 2] and list(fm.struct.col_sm) == [-1] * 4 and fm.struct.no_bsm == 1
+    rng = np.random.default_rng(1)
+    theta = rng.uniform(0.01, 1, (500, 3))
+    lnp, fr, st = hh.lnprob(fm, theta)
+    ref_fr = np.array([np.asarray(go.u_to_fr(t, go.NUFIT_U), dtype=float) for t in theta])
+    assert np.abs(fr - ref_fr).max() < 1e-14
+    ref = go.batch_multi_gaussian(ref_fr, go.angles_to_fr(g['asimov_angles']), 0.02)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lnp), fin) and np.max(np.abs(lnp[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-10
+    # scale invariance of the raw ratios
+    assert np.abs(hh.lnprob(fm, theta * 0.5)[1] - fr).max() < 1e-15
