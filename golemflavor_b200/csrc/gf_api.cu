@@ -117,6 +117,9 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
     memcpy(d->fixed_src, m->fixed_src, sizeof(d->fixed_src));
     memcpy(d->fixed_np, m->fixed_np, sizeof(d->fixed_np));
     d->fixed_loglam = m->fixed_loglam;
+    d->src_S = m->fixed_src[0] + m->fixed_src[1] + m->fixed_src[2];
+    d->src_sd0 = m->fixed_src[0] - m->fixed_src[2];
+    d->src_sd1 = m->fixed_src[1] - m->fixed_src[2];
     if (m->col_src[0] < 0 && m->col_x < 0 && m->col_src3[0] < 0) {
         const double s = m->fixed_src[0] + m->fixed_src[1] + m->fixed_src[2];
         GF_REQUIRE(isfinite(s) && s != 0.0, "model.fixed_src sums to %g", s);
@@ -137,6 +140,7 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
         const gfp_trig tn = gfp_angles_trig(m->fixed_np[0], m->fixed_np[1], m->fixed_np[2], m->fixed_np[3]);
         d->T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
         if (!d->np_free) GF_REQUIRE(isfinite(d->T.d0 + d->T.d1 + d->T.d2), "model.fixed_np does not describe mixing angles");
+        d->penT = gfp_make_pencil_T(d->T);
     }
 
     d->fr_bf[0] = m->fr_bf[0];

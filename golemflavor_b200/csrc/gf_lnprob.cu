@@ -24,7 +24,7 @@ extern std::atomic<unsigned long long> g_gf_launches;
 
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 
-template <int KIND>
+template <int KIND, int SPEC>
 __global__ void __launch_bounds__(GF_LP_THREADS, GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
@@ -39,10 +39,10 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_LP_MIN_BLOCKS)
     unsigned st = 0u;
     if (KIND == GF_K_FR) {
         gf_point q;
-        gf_resolve_point(m, get, q);
-        st = gf_point_fr(m, q, fr);
+        gf_resolve_point<SPEC>(m, get, q);
+        st = gf_point_fr<SPEC>(m, q, fr);
     } else {
-        lnp[i] = gf_point_lnprob(m, get, fr, st);
+        lnp[i] = gf_point_lnprob<SPEC>(m, get, fr, st);
     }
     if (fr_out) {
         fr_out[3 * i] = fr[0];
@@ -68,7 +68,10 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
     if (int rc = check_view(fn, model, d_theta, n, ld_point, ld_dim)) return rc;
     if (n == 0) return GF_OK;
     const gf_theta_view th{d_theta, ld_point, ld_dim};
-    k_lnprob<KIND><<<gf_blocks_for(n, GF_LP_THREADS), GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    if (KIND != GF_K_LNPRIOR && gf_model_is_fixed_spec(d))
+        k_lnprob<KIND, GF_SPEC_FIXED><<<gf_blocks_for(n, GF_LP_THREADS), GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    else
+        k_lnprob<KIND, GF_SPEC_GENERIC><<<gf_blocks_for(n, GF_LP_THREADS), GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     ++g_gf_launches;
     GF_LAUNCH_CHECK(fn);
     return GF_OK;
@@ -197,8 +200,12 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
         }
         GF_CUDA(cudaMemcpyAsync(p.d_theta[s], src, cnt * ndim * sizeof(double), cudaMemcpyHostToDevice, p.stream[s]));
         const gf_theta_view th{p.d_theta[s], ndim, 1};
-        k_lnprob<GF_K_LNPROB><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-            d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        if (gf_model_is_fixed_spec(d))
+            k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
+                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        else
+            k_lnprob<GF_K_LNPROB, GF_SPEC_GENERIC><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
+                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         ++g_gf_launches;
         GF_LAUNCH_CHECK("gf_lnprob_host");
         GF_CUDA(cudaMemcpyAsync(direct ? h_lnprob + off : p.s_lnp[s], p.d_lnp[s], cnt * sizeof(double), cudaMemcpyDeviceToHost, p.stream[s]));

@@ -18,6 +18,8 @@ struct gf_dev_model {
     int32_t col_sm[4], col_mass[2], col_src[2], col_np[4], col_scale, col_x, col_src3[3];
     double fixed_sm[4], fixed_mass[2], fixed_src[3], fixed_np[4], fixed_loglam;
     gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
+    gfp_pencil_T penT;          /* its pencil coefficients (fixed textures)              */
+    double src_S, src_sd0, src_sd1; /* fixed source: s0+s1+s2, s0-s2, s1-s2              */
     double wpoly[GFP_W_POLY_N]; /* cos(phi/3) polynomial, direct constant-bank operands  */
     double g[GF_MAX_BINS];      /* 2 Ec^(dim-2) 2^70: H*2E = H0 + 10^logLam g T          */
     double width[GF_MAX_BINS];  /* |E_hi - E_lo|                          (fr.py:414)    */
@@ -42,18 +44,32 @@ struct gf_point {
     double sm[4], mass[2], np[4], loglam, src[3];
 };
 
+/*
+ * Kernel specialisations (compile-time, chosen by the host from the model):
+ *   GF_SPEC_GENERIC : every model; which quantities are sampled is decided by uniform branches.
+ *   GF_SPEC_FIXED   : the production BSM shape -- fixed texture AND fixed source composition
+ *                     (scripts/fr.py, mc_texture.py).  The texture part of the pencil and the
+ *                     source constants are then read from the constant bank as direct DFMA operands:
+ *                     fewer registers and fewer three-register DFMAs (which issue at 2/3 rate on B200).
+ */
+#define GF_SPEC_GENERIC 0
+#define GF_SPEC_FIXED 1
+
+GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
+
 /* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
-template <class Get>
+template <int SPEC = GF_SPEC_GENERIC, class Get>
 GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
 #pragma unroll
     for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
-    if (m.np_free) {
+    if (SPEC != GF_SPEC_FIXED && m.np_free) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
     q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
+    if (SPEC == GF_SPEC_FIXED) return; /* source and NP mixing come from the constant bank */
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
     } else if (m.col_src3[0] >= 0) {
@@ -80,11 +96,42 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * The source normalisation 1/sum(s) and the 1/(E_max-E_min) factor cancel in the final
  * renormalisation and are not applied per bin.
  */
+/* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (Jacobi
+ * fallback), the transition in its four independent entries and the width-weighted sums. */
+template <class TPART>
+GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
+                           double lam, double s2, double sd0, double sd1, double S, double* fr) {
+    unsigned st = 0u;
+    double a0 = 0.0, a1 = 0.0, wsum = 0.0;
+    for (int b = 0; b < m.nbins; ++b) {
+        const double rho = lam * m.g[b];
+        gfp_x4 x;
+        if (!gfp_pencil_x4_fast(m.wpoly, pp, pt, rho, x)) {
+            gfp_x4 slow; /* separate object: keeps the fast path's x in registers */
+            st |= gfp_pencil_x4_jacobi(&h0, &T, rho, &slow);
+            x = slow;
+        }
+        double f0, f1;
+        gfp_mix4(x, s2, sd0, sd1, S, f0, f1);
+        const double wd = m.width[b];
+        a0 = fma(wd, f0, a0);
+        a1 = fma(wd, f1, a1);
+        wsum += wd;
+    }
+    /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is 1 / (S sum(width)) */
+    const double inv = 1.0 / (S * wsum);
+    fr[0] = a0 * inv;
+    fr[1] = a1 * inv;
+    fr[2] = 1.0 - fr[0] - fr[1];
+    return st;
+}
+
+template <int SPEC = GF_SPEC_GENERIC>
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
     unsigned st = 0u;
     const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
-    double X[9];
-    if (m.no_bsm) {
+    if (SPEC != GF_SPEC_FIXED && m.no_bsm) {
+        double X[9];
         gfp_pmns_abs2(t, X);
         double f[3];
         gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
@@ -97,42 +144,28 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
          * the polynomial invariants of the pencil H0 + rho T */
         gfp_herm3 h0 = gfp_herm_from_cols(u, q.mass[0] * GFP_MASS_SCALE, q.mass[1] * GFP_MASS_SCALE);
-        gfp_herm3 T;
-        if (m.np_free) {
-            const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
-            T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
-        } else {
-            T = m.T;
-        }
-        const gfp_pencil pen = gfp_make_pencil(h0, T);
 #ifdef __CUDA_ARCH__
         const double lam = exp10(q.loglam);
 #else
         const double lam = pow(10.0, q.loglam);
 #endif
-        const double S = q.src[0] + q.src[1] + q.src[2];
-        const double sd0 = q.src[0] - q.src[2], sd1 = q.src[1] - q.src[2];
-        double a0 = 0.0, a1 = 0.0, wsum = 0.0;
-        for (int b = 0; b < m.nbins; ++b) {
-            const double rho = lam * m.g[b];
-            gfp_x4 x;
-            if (!gfp_pencil_x4_fast(m.wpoly, pen, rho, x)) {
-                gfp_x4 slow; /* separate object: keeps the fast path's x in registers */
-                st |= gfp_pencil_x4_jacobi(&h0, &T, rho, &slow);
-                x = slow;
+        if (SPEC == GF_SPEC_FIXED) {
+            gfp_herm3 T = m.T;
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m.T, m.penT.te);
+            st = gf_bin_loop(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.src_S, fr);
+        } else {
+            gfp_herm3 T;
+            if (m.np_free) {
+                const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
+                T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
+            } else {
+                T = m.T;
             }
-            double f0, f1;
-            gfp_mix4(x, q.src[2], sd0, sd1, S, f0, f1);
-            const double wd = m.width[b];
-            a0 = fma(wd, f0, a0);
-            a1 = fma(wd, f1, a1);
-            wsum += wd;
+            const gfp_pencil_T pt = gfp_make_pencil_T(T);
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, T, pt.te);
+            st = gf_bin_loop(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2],
+                             q.src[0] + q.src[1] + q.src[2], fr);
         }
-        /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is 1 / (S sum(width)) */
-        const double inv = 1.0 / (S * wsum);
-        fr[0] = a0 * inv;
-        fr[1] = a1 * inv;
-        fr[2] = 1.0 - fr[0] - fr[1];
         /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
          * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
         const double mn = fmin(fr[0], fmin(fr[1], fr[2]));
@@ -140,6 +173,10 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
     }
     if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
     return st;
+}
+
+GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) {
+    return !m.no_bsm && !m.np_free && m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0;
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside. */
@@ -168,7 +205,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 }
 
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
-template <class Get>
+template <int SPEC = GF_SPEC_GENERIC, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
     const double lp = gf_point_lnprior(m, get);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
@@ -177,8 +214,8 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
         return (lp != lp) ? NAN : -INFINITY;
     }
     gf_point q;
-    gf_resolve_point(m, get, q);
-    st = gf_point_fr(m, q, fr);
+    gf_resolve_point<SPEC>(m, get, q);
+    st = gf_point_fr<SPEC>(m, q, fr);
     /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
     if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
     return lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);

@@ -22,8 +22,8 @@ extern std::atomic<unsigned long long> g_gf_launches;
 /* ------------------------------------------------------------------ kernels */
 
 /* Source of compositions: drawn samples (SCAN) or a given array (GIVEN). */
-template <bool SCAN, bool SMEM_HIST>
-__global__ void __launch_bounds__(GF_SCAN_THREADS)
+template <bool SCAN, bool SMEM_HIST, int SPEC>
+__global__ void __launch_bounds__(GF_SCAN_THREADS, 2) /* <= 128 registers: two 256-thread blocks (2 x 70 KB histograms) per SM */
     k_hist(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
            const double* __restrict__ fr_in, const int nb1, const double step, unsigned long long* __restrict__ hist,
            unsigned long long* __restrict__ accepted) {
@@ -41,8 +41,8 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS)
             double theta[GF_MAX_DIM];
             gf_draw_theta(m, seed, first_index + j, theta);
             gf_point q;
-            gf_resolve_point(m, [&](int k) { return theta[k]; }, q);
-            gf_point_fr(m, q, fr);
+            gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
+            gf_point_fr<SPEC>(m, q, fr);
         } else {
             fr[0] = fr_in[3 * j];
             fr[1] = fr_in[3 * j + 1];
@@ -112,8 +112,9 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     const bool use_smem = smem <= kSmemHistLimit;
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
-    auto kern_s = k_hist<SCAN, true>;
-    auto kern_g = k_hist<SCAN, false>;
+    const bool fixed = SCAN && gf_model_is_fixed_spec(d);
+    auto kern_s = fixed ? k_hist<SCAN, true, GF_SPEC_FIXED> : k_hist<SCAN, true, GF_SPEC_GENERIC>;
+    auto kern_g = fixed ? k_hist<SCAN, false, GF_SPEC_FIXED> : k_hist<SCAN, false, GF_SPEC_GENERIC>;
     int per_sm = 1;
     if (use_smem) {
         GF_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -36,20 +36,20 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def lnprob(fm, theta):
+def lnprob(fm, theta, spec=-1):
     th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
     n = th.shape[0]
     lnp, fr, st = np.empty(n), np.empty((n, 3)), np.empty(n, dtype=np.uint8)
-    rc = load().hh_lnprob(fm.ref, _p(th), C.c_int64(n), _p(lnp), _p(fr), _p(st))
+    rc = load().hh_lnprob(fm.ref, _p(th), C.c_int64(n), _p(lnp), _p(fr), _p(st), C.c_int(spec))
     _lib.check(rc)
     return lnp, fr, st
 
 
-def fr(fm, theta):
+def fr(fm, theta, spec=-1):
     th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
     n = th.shape[0]
     out, st = np.empty((n, 3)), np.empty(n, dtype=np.uint8)
-    _lib.check(load().hh_fr(fm.ref, _p(th), C.c_int64(n), _p(out), _p(st)))
+    _lib.check(load().hh_fr(fm.ref, _p(th), C.c_int64(n), _p(out), _p(st), C.c_int(spec)))
     return out, st
 
 

@@ -15,28 +15,39 @@
 #include "../../golemflavor_b200/csrc/gf_common.cuh"
 #include "../../golemflavor_b200/csrc/gf_ensemble_dev.cuh"
 
-extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st) {
+/* spec < 0: choose like the library does (FIXED specialisation when the model is eligible) */
+static bool use_fixed(const gf_dev_model& d, int spec) { return spec < 0 ? gf_model_is_fixed_spec(d) : spec == GF_SPEC_FIXED; }
+
+extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st, int spec) {
     gf_dev_model d;
     if (int rc = gf_build_dev_model(model, &d)) return rc;
+    const bool fixed = use_fixed(d, spec);
     for (int64_t i = 0; i < n; ++i) {
         auto get = [&](int k) { return theta[i * d.ndim + k]; };
         unsigned s = 0u;
         double f[3];
-        lnp[i] = gf_point_lnprob(d, get, f, s);
+        lnp[i] = fixed ? gf_point_lnprob<GF_SPEC_FIXED>(d, get, f, s) : gf_point_lnprob<GF_SPEC_GENERIC>(d, get, f, s);
         if (fr) memcpy(fr + 3 * i, f, sizeof(f));
         if (st) st[i] = (uint8_t)s;
     }
     return 0;
 }
 
-extern "C" int hh_fr(const gf_model* model, const double* theta, int64_t n, double* fr, uint8_t* st) {
+extern "C" int hh_fr(const gf_model* model, const double* theta, int64_t n, double* fr, uint8_t* st, int spec) {
     gf_dev_model d;
     if (int rc = gf_build_dev_model(model, &d)) return rc;
+    const bool fixed = use_fixed(d, spec);
     for (int64_t i = 0; i < n; ++i) {
         auto get = [&](int k) { return theta[i * d.ndim + k]; };
         gf_point q;
-        gf_resolve_point(d, get, q);
-        const unsigned s = gf_point_fr(d, q, fr + 3 * i);
+        unsigned s;
+        if (fixed) {
+            gf_resolve_point<GF_SPEC_FIXED>(d, get, q);
+            s = gf_point_fr<GF_SPEC_FIXED>(d, q, fr + 3 * i);
+        } else {
+            gf_resolve_point<GF_SPEC_GENERIC>(d, get, q);
+            s = gf_point_fr<GF_SPEC_GENERIC>(d, q, fr + 3 * i);
+        }
         if (st) st[i] = (uint8_t)s;
     }
     return 0;

@@ -240,8 +240,9 @@ def test_harness_flux_averaged_fr_matches_reference_and_mpmath(golden):
                 if tex != 'NONE':  # same answer through the fixed-texture (constant T) path
                     fm7 = model.flatten(models.bsm_args(dim, Texture[tex], src), None, models.bsm7_paramset(dim), likelihood='FLAT')
                     th7 = np.delete(g['theta'][sel], [6, 7, 8, 9], axis=1)
-                    fr7, _ = hh.fr(fm7, th7)
-                    assert np.abs(fr7 - fr).max() < 1e-13
+                    fr7, _ = hh.fr(fm7, th7)            # FIXED specialisation (texture + source in constants)
+                    fr7g, _ = hh.fr(fm7, th7, spec=0)   # same model through the generic path
+                    assert np.abs(fr7 - fr).max() < 1e-13 and np.abs(fr7g - fr7).max() < 1e-13
     assert worst_mp < 1e-10, worst_mp     # vs mpmath truth, everywhere (abs. error on a unit-sum composition)
     assert worst_ref < 1e-10, worst_ref   # vs the reference where the reference itself is accurate
 
