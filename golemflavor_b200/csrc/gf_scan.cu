@@ -49,12 +49,15 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, 2) /* <= 128 registers: two 2
             fr[2] = fr_in[3 * j + 2];
         }
         const int cell = gf_cell_index(fr, nb1, step);
-        if (cell >= 0) {
-            ++kept;
-            if (SMEM_HIST)
-                atomicAdd(&sh_hist[cell], 1u);
-            else
-                atomicAdd(&hist[cell], 1ull);
+        if (cell >= 0) ++kept;
+        if (SMEM_HIST) {
+            if (cell >= 0) atomicAdd(&sh_hist[cell], 1u);
+        } else {
+            /* no block-private copy for oversampled grids: aggregate equal cells inside the warp
+             * first (prior scans put most samples into a handful of cells, and L2 serialises atomics
+             * per address), one 64-bit atomic per distinct cell and warp */
+            const unsigned peers = __match_any_sync(__activemask(), cell);
+            if (cell >= 0 && (threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[cell], (unsigned long long)__popc(peers));
         }
     }
     if (SMEM_HIST) {
@@ -169,5 +172,213 @@ extern "C" int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg,
         d, cfg->seed, cfg->first_index, cfg->count, d_theta, d_fr, d_status);
     ++g_gf_launches;
     GF_LAUNCH_CHECK("gf_scan_samples");
+    return GF_OK;
+}
+
+/* ------------------------------------------------------------------ coverage region (plot.py:372-384) */
+
+/* out[0] += sum of counts > c, out[1] += #cells with count == c, out[2] = max count, out[3] += total,
+ * out[4] += #cells with count > c */
+__global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long c,
+                                                    unsigned long long* __restrict__ out) {
+    unsigned long long gt = 0ull, eq = 0ull, mx = 0ull, tot = 0ull, ngt = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = hist[i];
+        gt += v > c ? v : 0ull;
+        ngt += v > c ? 1ull : 0ull;
+        eq += v == c ? 1ull : 0ull;
+        mx = v > mx ? v : mx;
+        tot += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        gt += __shfl_down_sync(0xffffffffu, gt, o);
+        ngt += __shfl_down_sync(0xffffffffu, ngt, o);
+        eq += __shfl_down_sync(0xffffffffu, eq, o);
+        tot += __shfl_down_sync(0xffffffffu, tot, o);
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (gt) atomicAdd(out, gt);
+        if (eq) atomicAdd(out + 1, eq);
+        atomicMax(out + 2, mx);
+        if (tot) atomicAdd(out + 3, tot);
+        if (ngt) atomicAdd(out + 4, ngt);
+    }
+}
+
+/* one block walks the cells in order: mask = count > c, plus the first `take` cells with count == c */
+__global__ void __launch_bounds__(1024) k_cov_mask(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long c,
+                                                   unsigned long long take, uint8_t* __restrict__ mask) {
+    __shared__ unsigned int warp_ties[32];
+    __shared__ unsigned long long base;
+    if (threadIdx.x == 0) base = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t start = 0; start < cells; start += blockDim.x) {
+        const int64_t i = start + threadIdx.x;
+        const unsigned long long v = i < cells ? hist[i] : 0ull;
+        const bool tie = i < cells && v == c && c > 0ull;
+        const unsigned ballot = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) warp_ties[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned before = __popc(ballot & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += warp_ties[w];
+        const unsigned long long rank = base + before; /* number of tied cells ahead of this one */
+        if (i < cells) mask[i] = (v > c || (tie && rank < take)) ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_ties[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells, double coverage_percent, uint8_t* d_mask,
+                                unsigned long long* h_info, void* stream) {
+    GF_REQUIRE(cells >= 1 && d_hist && d_mask, "gf_coverage_mask: bad arguments");
+    GF_REQUIRE(coverage_percent >= 0.0 && coverage_percent <= 100.0, "gf_coverage_mask: coverage = %g outside [0, 100]", coverage_percent);
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    const int64_t want = (cells + 255) / 256;
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    unsigned long long* d_out = nullptr;
+    GF_CUDA(cudaMalloc(&d_out, 5 * sizeof(unsigned long long)));
+    unsigned long long h[5] = {0, 0, 0, 0, 0};
+    /* G(c) = sum of the counts > c; one multi-block reduction per evaluation */
+    auto pass = [&](unsigned long long c) -> int {
+        GF_CUDA(cudaMemsetAsync(d_out, 0, 5 * sizeof(unsigned long long), st));
+        k_cov_reduce<<<blocks, 256, 0, st>>>(d_hist, cells, c, d_out);
+        ++g_gf_launches;
+        GF_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+        GF_CUDA(cudaStreamSynchronize(st));
+        return GF_OK;
+    };
+    auto finish = [&](int rc) -> int {
+        cudaFree(d_out);
+        return rc;
+    };
+    if (int rc = pass(0ull)) return finish(rc);
+    const unsigned long long total = h[3], vmax = h[2];
+    const double need = coverage_percent / 100.0 * (double)total;
+    unsigned long long cstar = vmax, take = 0ull, n_gt = 0ull;
+    if (total > 0ull && need > 0.0) {
+        /* sorted by content, a cell is inside while the inclusive cumulative sum stays < need:
+         * c* = min{c : G(c) < need} is the content of the first excluded cell; G(0) = total >= need */
+        unsigned long long lo = 0ull, hi = vmax;
+        while (hi - lo > 1ull) {
+            const unsigned long long mid = lo + (hi - lo) / 2ull;
+            if (int rc = pass(mid)) return finish(rc);
+            if ((double)h[0] < need) hi = mid; else lo = mid;
+        }
+        cstar = hi;
+        if (int rc = pass(cstar)) return finish(rc);
+        const double g = (double)h[0];
+        n_gt = h[4];
+        /* tied cells j = 1, 2, ... are inside while g + j c* < need */
+        unsigned long long m = (unsigned long long)floor((need - g) / (double)cstar);
+        while (g + (double)(m + 1ull) * (double)cstar < need) ++m;
+        while (m > 0ull && !(g + (double)m * (double)cstar < need)) --m;
+        take = m < h[1] ? m : h[1];
+    }
+    if (total > 0ull && need > 0.0) {
+        k_cov_mask<<<1, 1024, 0, st>>>(d_hist, cells, cstar, take, d_mask);
+        ++g_gf_launches;
+    } else {
+        GF_CUDA(cudaMemsetAsync(d_mask, 0, (size_t)cells, st));
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return finish(gf_fail(GF_ERR_CUDA, "gf_coverage_mask: %s", cudaGetErrorString(e)));
+    if (h_info) {
+        h_info[0] = cstar;
+        h_info[1] = n_gt + take;
+        h_info[2] = take;
+    }
+    cudaStreamSynchronize(st);
+    return finish(GF_OK);
+}
+
+/* ------------------------------------------------------------------ Monte-Carlo evidence */
+
+__device__ __forceinline__ void gf_lse_merge(double& m, double& s, double m2, double s2) {
+    /* (m, s) <- log-sum-exp merge of two partials; empty partials are (-inf, 0) */
+    const double mm = fmax(m, m2);
+    if (mm == -INFINITY) {
+        m = -INFINITY;
+        s = 0.0;
+        return;
+    }
+    s = s * exp(m - mm) + s2 * exp(m2 - mm);
+    m = mm;
+}
+
+template <int SPEC>
+__global__ void __launch_bounds__(GF_SCAN_THREADS, 2)
+    k_evidence(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
+               double* __restrict__ partials /*[gridDim.x][2]*/) {
+    __shared__ double sh_m[GF_SCAN_THREADS / 32], sh_s[GF_SCAN_THREADS / 32];
+    double mx = -INFINITY, sm = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+        double theta[GF_MAX_DIM], fr[3];
+        gf_draw_theta(m, seed, first_index + j, theta);
+        gf_point q;
+        gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
+        gf_point_fr<SPEC>(m, q, fr);
+        const double ll = m.llh_kind == GF_LLH_FLAT
+                              ? m.llh_const
+                              : gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
+        if (ll == ll) gf_lse_merge(mx, sm, ll, 1.0); /* NaN samples carry no weight */
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_down_sync(0xffffffffu, mx, o), s2 = __shfl_down_sync(0xffffffffu, sm, o);
+        gf_lse_merge(mx, sm, m2, s2);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        sh_m[warp] = mx;
+        sh_s[warp] = sm;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < GF_SCAN_THREADS / 32; ++w) gf_lse_merge(mx, sm, sh_m[w], sh_s[w]);
+        partials[2 * blockIdx.x] = mx;
+        partials[2 * blockIdx.x + 1] = sm;
+    }
+}
+
+__global__ void k_lse_finish(const double* __restrict__ partials, int n, double* __restrict__ lse) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mx = lse[0], sm = lse[1];
+    for (int b = 0; b < n; ++b) gf_lse_merge(mx, sm, partials[2 * b], partials[2 * b + 1]); /* fixed order: deterministic */
+    lse[0] = mx;
+    lse[1] = sm;
+}
+
+extern "C" int gf_scan_evidence(const gf_model* model, const gf_scan_config* cfg, double* d_lse, void* stream) {
+    GF_REQUIRE(cfg != nullptr && d_lse != nullptr, "gf_scan_evidence: null pointer");
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    if (cfg->count == 0) return GF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    const bool fixed = gf_model_is_fixed_spec(d);
+    auto kern = fixed ? k_evidence<GF_SPEC_FIXED> : k_evidence<GF_SPEC_GENERIC>;
+    int per_sm = 1;
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GF_SCAN_THREADS, 0));
+    const uint64_t want = (cfg->count + GF_SCAN_THREADS - 1) / GF_SCAN_THREADS, persistent = (uint64_t)sms * (per_sm > 0 ? per_sm : 1);
+    const unsigned blocks = (unsigned)(want < persistent ? want : persistent);
+    double* d_part = nullptr;
+    GF_CUDA(cudaMallocAsync(&d_part, 2 * sizeof(double) * blocks, st));
+    kern<<<blocks, GF_SCAN_THREADS, 0, st>>>(d, cfg->seed, cfg->first_index, cfg->count, d_part);
+    k_lse_finish<<<1, 32, 0, st>>>(d_part, (int)blocks, d_lse);
+    g_gf_launches += 2;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(d_part, st);
+    if (e != cudaSuccess) return gf_fail(GF_ERR_CUDA, "gf_scan_evidence: %s", cudaGetErrorString(e));
     return GF_OK;
 }

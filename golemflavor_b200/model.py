@@ -127,7 +127,8 @@ def flatten(args, asimov_paramset, llh_paramset, likelihood=None):
     scale_cols = [k for k, t in enumerate(tags) if t == 'SCALE']
     np_cols = [k for k, t in enumerate(tags) if t == 'MMANGLES']
     src_cols = [k for k, t in enumerate(tags) if t == 'SRCANGLES']
-    no_bsm = bool(getattr(args, 'no_bsm', False)) or not scale_cols
+    fixed_scale = getattr(args, 'fixed_scale', None)   # sens.py:261-266: the scale is frozen at a grid value
+    no_bsm = bool(getattr(args, 'no_bsm', False)) or (not scale_cols and fixed_scale is None)
 
     if len(src_cols) == 1:
         m.col_x = src_cols[0]  # scripts/mc_x.py:187: a single SRCANGLES param x, source = (x, 1-x, 0)
@@ -152,9 +153,12 @@ def flatten(args, asimov_paramset, llh_paramset, likelihood=None):
             # paramset order, like the list comprehensions of fr.py:428-433
             m.col_sm[:] = [k for k, n in enumerate(names) if n in SM_ANGLE_NAMES]
             m.col_mass[:] = [k for k, n in enumerate(names) if n in MASS_NAMES]
-        if len(scale_cols) != 1:
+        if fixed_scale is not None and not scale_cols:
+            m.fixed_loglam = float(fixed_scale)
+        elif len(scale_cols) != 1:
             raise ValueError('expected one SCALE param, got {0}'.format(len(scale_cols)))
-        m.col_scale = scale_cols[0]
+        else:
+            m.col_scale = scale_cols[0]
         texture = enum_name(getattr(args, 'texture', None))
         if texture in TEXTURE_ANGLES:
             m.fixed_np[:] = TEXTURE_ANGLES[texture]

@@ -21,7 +21,7 @@ from .enums import ParamTag, PriorsCateg, Texture, enum_name
 from .param import Param, ParamSet
 
 __all__ = ['sm_paramset', 'scan_paramset', 'scan_model', 'scan_histogram', 'scan_samples', 'ternary_histogram',
-           'shard_range', 'allreduce_counts']
+           'shard_range', 'allreduce_counts', 'coverage_mask', 'scan_evidence']
 
 DEFAULT_BINNING = np.logspace(np.log10(6e4), np.log10(1e7), 21)  # fr.py:283-285
 
@@ -166,3 +166,42 @@ def ternary_histogram(frs, nb=25, return_tensor=False):
     _lib.check(_lib.load().gf_ternary_hist(_lib.ptr(f), f.shape[0], int(nb), _lib.ptr(hist), _lib.stream_ptr(torch)))
     h = hist.reshape(nb + 1, nb + 1, nb + 1)
     return h if return_tensor else h.cpu().numpy()
+
+
+def coverage_mask(hist, coverage, return_tensor=False):
+    """Highest-density region of a ternary histogram holding ``coverage`` per cent of the samples
+    (``plot.flavor_contour``, ``plot.py:372-384``).  Returns ``(mask, info)``: ``mask`` has the shape of
+    ``hist`` (1 inside the region); ``info = (content of the first excluded cell, number of masked
+    cells, number of masked cells tied with the first excluded one)``."""
+    torch = _lib.torch_cuda()
+    if isinstance(hist, torch.Tensor):
+        h = hist.to(device='cuda', dtype=torch.int64).contiguous()
+    else:
+        h = torch.as_tensor(np.ascontiguousarray(hist, dtype=np.int64)).cuda()
+    mask = torch.empty(h.numel(), dtype=torch.uint8, device='cuda')
+    info = (C.c_uint64 * 3)()
+    _lib.check(_lib.load().gf_coverage_mask(_lib.ptr(h), h.numel(), float(coverage), _lib.ptr(mask), info, _lib.stream_ptr(torch)))
+    mask = mask.reshape(h.shape)
+    return (mask if return_tensor else mask.cpu().numpy()), tuple(int(x) for x in info)
+
+
+def scan_evidence(fm, count, seed=26, first_index=0, distributed=True):
+    """ln of the prior-mean likelihood, ln( (1/N) sum_i L(theta_i) ) with theta_i ~ priors: the
+    Monte-Carlo evidence of a model up to its theta-independent prior-volume constant (what
+    ``scripts/sens.py:232-294`` obtains from MultiNest per grid point).  Sharded over ranks like
+    ``scan_histogram``; the (max, sum-exp) partials of the ranks are merged with two all-reduces."""
+    torch = _lib.torch_cuda()
+    dist = _dist() if distributed else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    start, n = shard_range(count, rank, world, first_index)
+    lse = torch.tensor([-np.inf, 0.0], dtype=torch.float64, device='cuda')
+    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=0)
+    _lib.check(_lib.load().gf_scan_evidence(fm.ref, C.byref(cfg), _lib.ptr(lse), _lib.stream_ptr(torch)))
+    if dist and world > 1:
+        gmax = lse[:1].clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        part = lse[1:] * torch.exp(lse[:1] - gmax) if bool(torch.isfinite(gmax)) else lse[1:] * 0
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        lse = torch.cat([gmax, part])
+    m, s = (float(x) for x in lse.cpu())
+    return m + np.log(s) - np.log(count) if s > 0 else -np.inf

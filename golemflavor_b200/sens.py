@@ -21,7 +21,7 @@ from .mcmc import DeviceEnsembleSampler, flat_seed
 from .param import Param, ParamSet
 from .scan import DEFAULT_BINNING, _dist, shard_range, sm_paramset
 
-__all__ = ['scale_grid', 'sweep_paramset', 'sweep']
+__all__ = ['scale_grid', 'sweep_paramset', 'sweep', 'evidence_grid']
 
 
 def scale_grid(dimension, segments):
@@ -91,3 +91,25 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
     out = rows.cpu().numpy()
     return {'dimension': out[:, 0].astype(int), 'scale': out[:, 1], 'mean_lnprob': out[:, 2], 'max_lnprob': out[:, 3],
             'acceptance': out[:, 4], 'mean_fr': out[:, 5:8]}
+
+
+def evidence_grid(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, source_ratio=(1, 2, 0),
+                  injected_ratio=(1, 1, 1), smearing=0.02, samples=1_000_000, seed=26, binning=DEFAULT_BINNING):
+    """Monte-Carlo evidence per (dimension, scale) grid point (``scripts/sens.py:289-294`` stores
+    ``(scale, lnZ)`` per point): the six SM nuisance parameters are drawn from their priors, the scale is
+    frozen at the grid value, ``lnZ = ln mean(L)``.  Returns ``{dimension: array[segments, 2]}`` like the
+    reference's ``evidence_arr``; Bayes factors against the null point (scale -100) follow by subtraction
+    (``plot.get_limit``, ``plot.py:149-213``)."""
+    from .scan import scan_evidence
+    src = np.asarray(source_ratio, dtype=np.float64)
+    inj = np.asarray(injected_ratio, dtype=np.float64)
+    out = {}
+    for dim in dimensions:
+        rows = []
+        for scale in scale_grid(dim, segments):
+            args = Namespace(source_ratio=src / src.sum(), dimension=int(dim), texture=texture, binning=np.asarray(binning),
+                             no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing), fixed_scale=float(scale))
+            fm = _model.flatten(args, None, ParamSet(sm_paramset(with_mass=True)))
+            rows.append((scale, scan_evidence(fm, samples, seed=seed)))
+        out[int(dim)] = np.array(rows)
+    return out

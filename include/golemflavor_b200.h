@@ -195,6 +195,22 @@ int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg, double* d_
 /* Histogram of given compositions (bit-exact np.histogramdd), ADDS into d_hist. */
 int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsigned long long* d_hist, void* stream);
 
+/* Prior-sample Monte-Carlo evidence (the quantity scripts/sens.py:232-294 gets from MultiNest per
+ * (dimension, scale) grid point): draws `cfg->count` samples from the priors exactly like gf_scan_hist,
+ * evaluates the likelihood L (model.llh_kind) and accumulates log-sum-exp partials with warp shuffles:
+ * d_lse[0] = max ln L, d_lse[1] = sum exp(ln L - max), merged with the values already stored there
+ * (initialise to {-inf, 0}); ln mean(L) = d_lse[0] + log(d_lse[1]) - log(N).  cfg->nb is unused. */
+int gf_scan_evidence(const gf_model* model, const gf_scan_config* cfg, double* d_lse /*[2]*/, void* stream);
+/* Highest-density coverage region of a histogram (plot.flavor_contour, plot.py:372-384: normalise,
+ * sort cells by content, cumulative sum, `thres = searchsorted(cumsum, coverage/100)`, mask the first
+ * `thres` cells).  d_mask[i] = 1 for the cells inside the region.  h_info (host, optional) receives
+ * {count of the first excluded cell c*, number of masked cells, number of masked cells with count == c*}.
+ * Cells tied at c* are taken in flat-index order (the reference's order among ties is that of an
+ * unstable sort).  The 3-D Gaussian filter of plot.py:375 has sigma = 0.05 bins, i.e. a one-tap kernel:
+ * it is the identity and is not applied.  Synchronises `stream`. */
+int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells, double coverage_percent, uint8_t* d_mask,
+                     unsigned long long* h_info /*[3] or NULL*/, void* stream);
+
 /* ---- ensemble sampler --------------------------------------------------- */
 /*
  * Device-resident affine-invariant ensemble sampler: the stretch move of emcee's EnsembleSampler

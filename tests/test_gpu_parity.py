@@ -528,3 +528,57 @@ def test_sens_sweep_small(torch):
     # the null point (logLam = -100: no new physics) and the smallest in-range scale agree; the largest scale differs
     d6 = out['dimension'] == 6
     assert np.abs(out['mean_fr'][d6][0] - out['mean_fr'][d6][1]).max() < 0.05
+
+
+def test_coverage_mask_matches_reference_definition(torch):
+    """plot.flavor_contour's coverage region (plot.py:372-384) restated with NumPy vs gf_coverage_mask."""
+    fm = scan.scan_model('unitary', source_ratio=(1, 0, 0))
+    for nb, n in ((25, 2_000_000), (100, 500_000)):
+        hist, _ = scan.scan_histogram(fm, n, nb=nb, seed=3, distributed=False)
+        for cov in (68.0, 90.0, 99.0, 100.0, 0.0):
+            mask, (cstar, nmask, ntie) = scan.coverage_mask(hist, cov)
+            H = hist / hist.sum()                         # plot.py:371; gaussian_filter(sigma=0.05) is a one-tap identity
+            Hr = np.ravel(H)
+            order = np.argsort(Hr)[::-1]
+            thres = int(np.searchsorted(np.cumsum(Hr[order]), cov / 100.))
+            ref = np.zeros(Hr.shape)
+            ref[order[:thres]] = 1
+            flat, m = hist.ravel(), mask.ravel()
+            assert m.sum() == thres == nmask, (nb, cov, m.sum(), thres)
+            if thres in (0, len(flat)):
+                continue
+            first_out = flat[order[thres]]
+            assert cstar == first_out
+            assert np.array_equal(m[flat > cstar], ref[flat > cstar]) and np.all(m[flat > cstar] == 1)
+            assert np.all(m[flat < cstar] == 0) and m[flat == cstar].sum() == ntie == ref[flat == cstar].sum()
+    from scipy.ndimage import gaussian_filter
+    assert np.array_equal(gaussian_filter(H, sigma=0.05), H)   # the reference's smoothing really is the identity
+
+
+def test_scan_evidence_against_oracle(torch):
+    """ln mean(L) over prior draws: device log-sum-exp vs the oracle's likelihood on the same draws."""
+    from argparse import Namespace
+    from golemflavor_b200.param import ParamSet
+    args = Namespace(source_ratio=np.array([1, 2, 0.]) / 3, dimension=6, texture=Texture.OET, binning=models.BINNING, no_bsm=False,
+                     injected_ratio=[1 / 3, 1 / 3, 1 / 3], smearing=0.02, fixed_scale=-42.0)
+    fm = model.flatten(args, None, ParamSet(scan.sm_paramset(with_mass=True)))
+    assert fm.struct.col_scale == -1 and fm.struct.fixed_loglam == -42.0 and fm.struct.no_bsm == 0
+    n = 40000
+    theta, frs, _ = scan.scan_samples(fm, n, seed=26)
+    ref_fr = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], model.TEXTURE_ANGLES['OET'], np.full(n, -42.0), 6,
+                                         models.BINNING, args.source_ratio)
+    assert np.abs(frs - ref_fr).max() < FR_TOL
+    ll = go.batch_multi_gaussian(ref_fr, [1 / 3, 1 / 3, 1 / 3], 0.02)
+    fin = np.isfinite(ll)
+    mx = ll[fin].max()
+    ref = mx + np.log(np.exp(ll[fin] - mx).sum()) - np.log(n)
+    got = scan.scan_evidence(fm, n, seed=26, distributed=False)
+    assert abs(got - ref) < 1e-9 * abs(ref), (got, ref)
+    # shard invariance of the merge
+    parts = [scan.scan_evidence(fm, c, seed=26, first_index=s, distributed=False) + np.log(c) for s, c in ((0, 15000), (15000, 25000))]
+    both = np.logaddexp(parts[0], parts[1]) - np.log(n)
+    assert abs(both - got) < 1e-12 * abs(got)
+    # the null point (no new physics) has the same evidence for every dimension
+    from golemflavor_b200 import sens
+    ev = sens.evidence_grid(dimensions=(3, 6), segments=4, samples=20000)
+    assert ev[3].shape == (4, 2) and ev[3][0, 0] == -100 and abs(ev[3][0, 1] - ev[6][0, 1]) < 1e-9
