@@ -281,6 +281,44 @@ def run_gpu(opts):
                      'kept': int(kept.item()), 'hist_checksum': int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item()),
                      'collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
 
+    # -- secondary: the sampler-shaped configs of BASELINE.json (latency-bound by design: 512 / 2048 /
+    #    18000 points per half-step), run on the device-resident ensemble sampler
+    cfg_info = None
+    if opts.configs:
+        import models as _m
+        from golemflavor_b200 import mcmc, sens
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+        cfg_info = {}
+
+        def timed(fn_):
+            barrier()
+            t0_ = time.perf_counter()
+            r_ = fn_()
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0_), r_
+
+        a2, as2, ps2 = _m.notebook_model(g['asimov_angles'])
+        f2 = llh.LnProb(a2, as2, ps2)
+        np.random.seed(25)
+        p0 = mcmc.flat_seed(ps2, 1024)
+        p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
+        smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
+        smp.run_mcmc(p0, 200, store=False)
+        sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))
+        cfg_info['C2_emcee_sm_fit'] = {'walkers': 1024, 'steps': 10000, 'ndim': 6, 'seconds': sec, 'evals_per_s': 1024 * 1e4 / sec,
+                                       'acceptance': float(np.mean(smp.acceptance_fraction)), 'launches': 1,
+                                       'note': 'replicas only: every rank runs the same chain shape independently'}
+        p3 = mcmc.flat_seed(pset, 4096)
+        smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
+        smp3.run_mcmc(p3, 100, store=False)
+        sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
+        cfg_info['C3_bsm_dim6_fit'] = {'walkers': 4096, 'steps': 2000, 'ndim': fn.ndim, 'seconds': sec, 'evals_per_s': 4096 * 2000 / sec,
+                                       'acceptance': float(np.mean(smp3.acceptance_fraction))}
+        sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
+        cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
+                                     'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
+                                     'sharding': 'grid points split over %d rank(s), one all-reduce of the summaries' % world}
+
     if rank == 0:
         base = None
         if world == 1 and opts.cpu_evals > 0:
@@ -317,6 +355,7 @@ def run_gpu(opts):
             'gpu_launches': int(launches),
             'clocks': clock_info,
             'scan': scan_info,
+            'configs': cfg_info,
         }
         print(json.dumps(line))
     if world > 1:
@@ -331,6 +370,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-evals', type=int, default=1500, help='size of the bounded CPU-baseline sample (0 = skip)')
     ap.add_argument('--scan-samples', type=int, default=10 ** 10, help='samples of the secondary scan section (0 = skip)')
+    ap.add_argument('--configs', type=int, default=1, help='1: also time the sampler-shaped configs C2/C3/C5 (secondary section)')
     ap.add_argument('--scan-mode', default='anarchic', choices=['unitary', 'x', 'texture', 'anarchic'])
     opts = ap.parse_args()
     opts.warmup = max(opts.warmup, 3) if opts.impl == 'b200' else opts.warmup
