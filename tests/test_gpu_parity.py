@@ -584,3 +584,18 @@ def test_scan_evidence_against_oracle(torch):
     from golemflavor_b200 import sens
     ev = sens.evidence_grid(dimensions=(3, 6), segments=4, samples=20000)
     assert ev[3].shape == (4, 2) and ev[3][0, 0] == -100 and abs(ev[3][0, 1] - ev[6][0, 1]) < 1e-9
+
+
+def test_cli_scan_outputs(torch, tmp_path):
+    from golemflavor_b200 import cli
+    out = cli.main(['mc_unitary', '--nwalkers', '20', '--nsteps', '50', '--datadir', str(tmp_path)])
+    assert out.endswith('mc_unitary_SRC_1_2_0.npy')
+    frs = np.load(out)
+    assert frs.shape == (1000, 3) and np.abs(frs.sum(axis=1) - 1).max() < 1e-14          # mc_unitary.py:189-193
+    out = cli.main(['mc_texture', '--dimension', '6', '--texture', 'OET', '--nwalkers', '10', '--nsteps', '20', '--datadir', str(tmp_path)])
+    arr = np.load(out)
+    assert out.endswith('mc_texture_DIM6_SRC_1_2_0_OET.npy') and arr.shape == (200, 3 + 7)   # (frs, samples), mc_texture.py:222
+    ref = truth.eigh_flux_averaged_fr(arr[:, 3:7], arr[:, 7:9], model.TEXTURE_ANGLES['OET'], arr[:, 9], 6, models.BINNING, np.array([1, 2, 0.]) / 3)
+    assert np.abs(arr[:, :3] - ref).max() < FR_TOL
+    out = cli.main(['fr', '--dimension', '6', '--texture', 'OET', '--nwalkers', '32', '--burnin', '20', '--nsteps', '30', '--datadir', str(tmp_path)])
+    assert out.endswith('chain_DIM6_sfr_1_2_0_mfr_1_1_1_OET.npy') and np.load(out).shape == (32 * 30, 7)

@@ -372,3 +372,15 @@ def test_harness_config1_three_source_ratios_fixed_pmns(golden):
     assert np.array_equal(np.isfinite(lnp), fin) and np.max(np.abs(lnp[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-10
     # scale invariance of the raw ratios
     assert np.abs(hh.lnprob(fm, theta * 0.5)[1] - fr).max() < 1e-15
+
+
+def test_cli_identifiers_match_reference_naming():
+    from argparse import Namespace
+    from golemflavor_b200 import cli
+    assert cli.solve_ratio([1 / 3, 2 / 3, 0]) == '1_2_0' and cli.solve_ratio([1, 0, 0]) == '1_0_0'   # misc.py:34-41
+    assert cli.solve_ratio([0.3, 0.3, 0.4]) == '0.30_0.30_0.40'
+    a = Namespace(dimension=6, source_ratio=[1, 2, 0], injected_ratio=[1, 1, 1], texture=Texture.OET)
+    assert cli.gen_identifier(a, 'fr') == '_DIM6_sfr_1_2_0_mfr_1_1_1_OET'                              # misc.py:44-51
+    assert cli.gen_identifier(a, 'mc_texture') == '_DIM6_SRC_1_2_0_OET' and cli.gen_identifier(a, 'mc_unitary') == '_SRC_1_2_0'
+    ns = cli._parser().parse_args(['mc_texture', '--dimension', '6', '--texture', 'out', '--nwalkers', '10'])
+    assert ns.texture is Texture.OUT and ns.nwalkers == 10 and ns.binning == [6e4, 1e7, 20]
