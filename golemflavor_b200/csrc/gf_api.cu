@@ -91,8 +91,6 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
     d->llh_kind = m->llh_kind;
     GF_REQUIRE(m->llh_kind == GF_LLH_FLAT || m->llh_kind == GF_LLH_GAUSSIAN, "model.llh_kind = %d is not a GF_LLH_* value", m->llh_kind);
     d->emulate_underflow = m->emulate_underflow ? 1 : 0;
-    static const double wpoly[GFP_W_POLY_N] = GFP_W_POLY_INIT;
-    memcpy(d->wpoly, wpoly, sizeof(wpoly));
 
     struct { const int32_t* src; int32_t* dst; int n; const char* name; } cols[] = {
         {m->col_sm, d->col_sm, 4, "col_sm"},       {m->col_mass, d->col_mass, 2, "col_mass"},

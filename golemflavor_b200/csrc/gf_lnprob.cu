@@ -6,8 +6,13 @@
  * One parameter point per thread; the flattened model travels as a __grid_constant__ kernel
  * parameter (constant bank), theta is read through a strided view so that both the emcee
  * row-major layout and an SoA layout are served, everything else stays in registers.
- * The kernel is fp64-pipe bound (~3.0e3 DFMA-pipe instructions per point for 20 energy bins
- * against 64 B of traffic), see DESIGN.md.
+ * The kernel is fp64-pipe bound (~2.5e3 DFMA-pipe instructions per point for 20 energy bins
+ * against 64 B of traffic), see DESIGN.md.  theta is loaded directly (no shared-memory staging):
+ * an A/B test of a persistent-grid variant that double-buffered theta tiles through shared memory
+ * with cp.async was 1-12 % SLOWER the coarser its work granularity (0.787 ms at one 32-point tile
+ * per warp ... 0.874 ms fully persistent, vs 0.780 ms here) -- the exposed first-load latency is
+ * covered by other warps' arithmetic, while the hardware block scheduler's fine-grained dynamic
+ * balancing over SMs is worth more than the prefetch.
  */
 #include <atomic>
 #include <mutex>
@@ -17,9 +22,11 @@
 
 extern std::atomic<unsigned long long> g_gf_launches;
 
-#define GF_LP_THREADS 128
+#ifndef GF_LP_THREADS
+#define GF_LP_THREADS 64
+#endif
 #ifndef GF_LP_MIN_BLOCKS
-#define GF_LP_MIN_BLOCKS 4 /* resident blocks per SM the register allocation is tuned for */
+#define GF_LP_MIN_BLOCKS 8 /* resident blocks per SM the register allocation is tuned for */
 #endif
 
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
@@ -40,9 +47,9 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_LP_MIN_BLOCKS)
     if (KIND == GF_K_FR) {
         gf_point q;
         gf_resolve_point<SPEC>(m, get, q);
-        st = gf_point_fr<SPEC>(m, q, fr);
+        st = gf_point_fr<SPEC, 2>(m, q, fr);
     } else {
-        lnp[i] = gf_point_lnprob<SPEC>(m, get, fr, st);
+        lnp[i] = gf_point_lnprob<SPEC, 2>(m, get, fr, st);
     }
     if (fr_out) {
         fr_out[3 * i] = fr[0];

@@ -20,7 +20,6 @@ struct gf_dev_model {
     gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
     gfp_pencil_T penT;          /* its pencil coefficients (fixed textures)              */
     double src_S, src_sd0, src_sd1; /* fixed source: s0+s1+s2, s0-s2, s1-s2              */
-    double wpoly[GFP_W_POLY_N]; /* cos(phi/3) polynomial, direct constant-bank operands  */
     double g[GF_MAX_BINS];      /* 2 Ec^(dim-2) 2^70: H*2E = H0 + 10^logLam g T          */
     double width[GF_MAX_BINS];  /* |E_hi - E_lo|                          (fr.py:414)    */
     double fr_bf[3];
@@ -98,16 +97,45 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  */
 /* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (Jacobi
  * fallback), the transition in its four independent entries and the width-weighted sums. */
-template <class TPART>
+template <int ILP, class TPART>
 GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
                            double lam, double s2, double sd0, double sd1, double S, double* fr) {
     unsigned st = 0u;
     double a0 = 0.0, a1 = 0.0, wsum = 0.0;
-    for (int b = 0; b < m.nbins; ++b) {
+    /* ILP = 2: two bins per iteration, i.e. two independent fast-path chains in flight per thread
+     * (+10 % on k_lnprob, which is bound by the latency of that chain at 16 warps per SM); kernels with
+     * more per-thread state (the scans) keep ILP = 1 because the second chain would spill */
+    int b = 0;
+    for (; ILP == 2 && b + 1 < m.nbins; b += 2) {
+        const double rho0 = lam * m.g[b], rho1 = lam * m.g[b + 1];
+        gfp_x4 x0, x1;
+        const bool ok0 = gfp_pencil_x4_fast(pp, pt, rho0, x0);
+        const bool ok1 = gfp_pencil_x4_fast(pp, pt, rho1, x1);
+        if (!(ok0 && ok1)) { /* rare: Jacobi for whichever bin failed; separate objects keep x0/x1 in registers */
+            if (!ok0) {
+                gfp_x4 slow;
+                st |= gfp_pencil_x4_jacobi(&h0, &T, rho0, &slow);
+                x0 = slow;
+            }
+            if (!ok1) {
+                gfp_x4 slow;
+                st |= gfp_pencil_x4_jacobi(&h0, &T, rho1, &slow);
+                x1 = slow;
+            }
+        }
+        double f00, f01, f10, f11;
+        gfp_mix4(x0, s2, sd0, sd1, S, f00, f01);
+        gfp_mix4(x1, s2, sd0, sd1, S, f10, f11);
+        const double wd0 = m.width[b], wd1 = m.width[b + 1];
+        a0 = fma(wd1, f10, fma(wd0, f00, a0));
+        a1 = fma(wd1, f11, fma(wd0, f01, a1));
+        wsum += wd0 + wd1;
+    }
+    for (; b < m.nbins; ++b) { /* ILP = 1, or the last of an odd number of bins */
         const double rho = lam * m.g[b];
         gfp_x4 x;
-        if (!gfp_pencil_x4_fast(m.wpoly, pp, pt, rho, x)) {
-            gfp_x4 slow; /* separate object: keeps the fast path's x in registers */
+        if (!gfp_pencil_x4_fast(pp, pt, rho, x)) {
+            gfp_x4 slow;
             st |= gfp_pencil_x4_jacobi(&h0, &T, rho, &slow);
             x = slow;
         }
@@ -126,7 +154,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
     return st;
 }
 
-template <int SPEC = GF_SPEC_GENERIC>
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
     unsigned st = 0u;
     const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
@@ -152,7 +180,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         if (SPEC == GF_SPEC_FIXED) {
             gfp_herm3 T = m.T;
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m.T, m.penT.te);
-            st = gf_bin_loop(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.src_S, fr);
+            st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.src_S, fr);
         } else {
             gfp_herm3 T;
             if (m.np_free) {
@@ -163,7 +191,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
             }
             const gfp_pencil_T pt = gfp_make_pencil_T(T);
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, T, pt.te);
-            st = gf_bin_loop(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2],
+            st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2],
                              q.src[0] + q.src[1] + q.src[2], fr);
         }
         /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
@@ -205,7 +233,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 }
 
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
-template <int SPEC = GF_SPEC_GENERIC, class Get>
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
     const double lp = gf_point_lnprior(m, get);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
@@ -215,7 +243,7 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
     }
     gf_point q;
     gf_resolve_point<SPEC>(m, get, q);
-    st = gf_point_fr<SPEC>(m, q, fr);
+    st = gf_point_fr<SPEC, ILP>(m, q, fr);
     /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
     if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
     return lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);

@@ -17,7 +17,7 @@
  * The reference evaluates these in x87 80-bit arithmetic with a cancellation-prone
  * eigenvector formula.  Here the eigen stage works on the trace-free, norm-scaled
  * matrix: eigenvalues by the trigonometric (Cardano) solution with the cos(phi/3)
- * branch obtained trig-free from a minimax polynomial, squared eigenvector moduli
+ * branch obtained trig-free (fp32-seeded Newton on the cubic), squared eigenvector moduli
  * from the eigenvector-eigenvalue identity, and a cyclic complex Jacobi solver as
  * the fallback whenever two eigenvalues approach each other.
  */
@@ -88,31 +88,40 @@ struct gfp_herm3 {
 };
 
 /*
- * w(delta)/delta on delta in [0,1], where w = 1 - cos(phi/3) is the smallest root of
- * 4w^3 - 12w^2 + 9w = delta and delta = 1 - |cos(phi)|.  Degree-20 fit (Chebyshev interpolation,
- * relative error < 2.3e-16) in t = 2 delta - 1, generated by scratch/fit_w.py; coefficient k
- * multiplies t^k.  This replaces acos + cos of the reference's trigonometric root formula
- * (fr.py:216-221) and keeps full RELATIVE accuracy of w as delta -> 0.  The table travels inside
- * the kernel parameter (constant bank), so that every coefficient is a direct DFMA operand.
+ * w = 1 - cos(phi/3): the smallest root of g(w) = 4w^3 - 12w^2 + 9w - delta with delta = 1 - |cos(phi)|
+ * in [0, 1] (w in [0, 0.134]).  This replaces acos + cos of the reference's trigonometric root formula
+ * (fr.py:216-221) and keeps full RELATIVE accuracy of w as delta -> 0 (near-degenerate pairs).
+ *
+ * The fp64 pipe is the bottleneck of every kernel here while the fp32 pipe idles, so the root is
+ * SEEDED in single precision -- a degree-6 polynomial for w/delta (Chebyshev fit in t = 2 delta - 1,
+ * scratch/fit_w32.py, relative error 3.4e-7) and the reciprocal slope r ~ 1/g'(w0) -- and polished by
+ * two fp64 Newton steps with the frozen slope, w <- w - r g(w).  Error recursion e' = e (1 - r g') +
+ * O(e^2): 3.4e-7 -> 9e-14 -> 2e-20 relative, i.e. fp64 rounding of g (~eps * w) is what remains.
+ * 8 fp64 operations instead of the 23 of a full-precision degree-20 polynomial.
  */
-#define GFP_W_POLY_N 21
-#define GFP_W_POLY_INIT                                                                                      \
-    {1.20614758428183227e-01, 1.10288561167162548e-02, 1.83397185861192006e-03, 3.79338053063842768e-04,     \
-     8.79525057641045480e-05, 2.18763314757019913e-05, 5.70622510515210637e-06, 1.54035419892792902e-06,     \
-     4.26720748563536802e-07, 1.20632116849623665e-07, 3.46614029118410834e-08, 1.00930942051318683e-08,     \
-     2.97198724668838339e-09, 8.83562014460692177e-10, 2.64784627467715323e-10, 7.96948955002133062e-11,     \
-     2.41982419679814614e-11, 7.62929460857843359e-12, 2.34229570042012674e-12, 5.52634478083809797e-13,     \
-     1.70284352804893418e-13}
-
-/* Even/odd split (two independent Horner chains in t^2): half the dependent-DFMA latency. */
-GF_HD double gfp_cubic_w_over_delta(const double* c /*[GFP_W_POLY_N]*/, double t) {
-    const double t2 = t * t;
-    double pe = c[20], po = c[19];
-#pragma unroll
-    for (int k = 18; k >= 0; k -= 2) pe = fma(pe, t2, c[k]);
-#pragma unroll
-    for (int k = 17; k >= 1; k -= 2) po = fma(po, t2, c[k]);
-    return fma(po, t, pe);
+GF_HD double gfp_cubic_w(double delta) {
+    const float d = (float)delta;
+    const float t = fmaf(2.0f, d, -1.0f);
+    float p = 6.536684850e-06f;
+    p = fmaf(p, t, 2.486253834e-05f);
+    p = fmaf(p, t, 8.752417489e-05f);
+    p = fmaf(p, t, 3.777995007e-04f);
+    p = fmaf(p, t, 1.834025956e-03f);
+    p = fmaf(p, t, 1.102905069e-02f);
+    p = fmaf(p, t, 1.206147596e-01f);
+    const float w0 = d * p;
+    const float slope = fmaf(fmaf(12.0f, w0, -24.0f), w0, 9.0f); /* g'(w0) in [6, 9] */
+#ifdef __CUDA_ARCH__
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(slope));
+#else
+    const float rf = 1.0f / slope;
+#endif
+    const double r = (double)rf;
+    double w = (double)w0;
+    w = fma(-r, fma(fma(fma(4.0, w, -12.0), w, 9.0), w, -delta), w);
+    w = fma(-r, fma(fma(fma(4.0, w, -12.0), w, 9.0), w, -delta), w);
+    return w;
 }
 
 /* The four independent entries of the doubly stochastic matrix |V_ai|^2:
@@ -131,15 +140,16 @@ struct gfp_x4 {
  * pair is nearer than the fast-path limit or the input is degenerate / non-finite; the caller then
  * runs the Jacobi fallback.
  */
-GF_HD bool gfp_eig_core(const double* wpoly, double e0, double e1, double e2, double a2, double b2, double c2, double Q, double det,
-                        gfp_x4& out) {
-    if (!(Q > 1e-280)) return false; /* also catches NaN */
+GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, double c2, double Q, double det, gfp_x4& out) {
+    /* Straight-line code on purpose (no early exit): the caller evaluates two energy bins back to
+     * back and the compiler interleaves their independent dependency chains -- with 16 resident warps
+     * per SM the kernels are bound by the latency of this chain, not by fp64 issue.  Degenerate or
+     * non-finite inputs simply produce garbage that the returned flag tells the caller to discard. */
     const double rs = gfp_rsqrt(Q);
     const double r = (0.5 * det * rs) * (rs * rs); /* cos(phi) */
-    const double delta = 1.0 - fabs(r); /* a rounding-negative delta gives s2 < 0 and takes the fallback */
-    const double w = delta * gfp_cubic_w_over_delta(wpoly, fma(2.0, delta, -1.0));
+    const double delta = 1.0 - fabs(r);            /* a rounding-negative delta gives s2 < 0 and takes the fallback */
+    const double w = gfp_cubic_w(delta);
     const double s2 = w * (2.0 - w); /* sin^2(phi/3) */
-    if (!(s2 >= GFP_FAST_MIN_SIN2)) return false;
     const double sq = 2.0 * Q * rs;                     /* 2 sqrt(Q) */
     const double l0 = copysign(sq - sq * w, r);         /* 2 sqrt(Q) cos(phi/3), isolated eigenvalue */
     const double half_gap = (0.8660254037844386 * sq) * (s2 * gfp_rsqrt(s2));
@@ -159,11 +169,12 @@ GF_HD bool gfp_eig_core(const double* wpoly, double e0, double e1, double e2, do
     out.x10 = n10 * i0;
     out.x01 = n01 * i1;
     out.x11 = n11 * i1;
-    return true;
+    /* Q > tiny also rejects NaN; s2 >= limit rejects close pairs, NaN and negative round-off */
+    return (Q > 1e-280) && (s2 >= GFP_FAST_MIN_SIN2);
 }
 
 /* Invariants of one matrix computed directly (single-matrix entry points and tests). */
-GF_HD bool gfp_herm3_x4_fast(const double* wpoly, const gfp_herm3& h, gfp_x4& out) {
+GF_HD bool gfp_herm3_x4_fast(const gfp_herm3& h, gfp_x4& out) {
     const double mu = (h.d0 + h.d1 + h.d2) * (1.0 / 3.0);
     const double e0 = h.d0 - mu, e1 = h.d1 - mu, e2 = h.d2 - mu;
     const double a2 = fma(h.ar, h.ar, h.ai * h.ai);
@@ -175,7 +186,7 @@ GF_HD bool gfp_herm3_x4_fast(const double* wpoly, const gfp_herm3& h, gfp_x4& ou
     const double aci = fma(h.ar, h.ci, h.ai * h.cr);
     const double tri = fma(acr, h.br, aci * h.bi);
     const double det = fma(2.0, tri, e0 * e1 * e2) - fma(e0, c2, fma(e1, b2, e2 * a2));
-    return gfp_eig_core(wpoly, e0, e1, e2, a2, b2, c2, p2 * (1.0 / 6.0), det, out);
+    return gfp_eig_core(e0, e1, e2, a2, b2, c2, p2 * (1.0 / 6.0), det, out);
 }
 
 /*
@@ -249,14 +260,14 @@ GF_HD gfp_pencil_P gfp_make_pencil_P(const gfp_herm3& h0, const gfp_herm3& T, co
     return p;
 }
 
-GF_HD bool gfp_pencil_x4_fast(const double* wpoly, const gfp_pencil_P& p, const gfp_pencil_T& t, double rho, gfp_x4& out) {
+GF_HD bool gfp_pencil_x4_fast(const gfp_pencil_P& p, const gfp_pencil_T& t, double rho, gfp_x4& out) {
     const double e0 = fma(rho, t.te[0], p.e[0]), e1 = fma(rho, t.te[1], p.e[1]), e2 = fma(rho, t.te[2], p.e[2]);
     const double a2 = fma(fma(t.a22, rho, p.a2[1]), rho, p.a2[0]);
     const double b2 = fma(fma(t.b22, rho, p.b2[1]), rho, p.b2[0]);
     const double c2 = fma(fma(t.c22, rho, p.c2[1]), rho, p.c2[0]);
     const double Q = fma(fma(t.q2, rho, p.q[1]), rho, p.q[0]);
     const double det = fma(fma(fma(t.d3, rho, p.d[2]), rho, p.d[1]), rho, p.d[0]);
-    return gfp_eig_core(wpoly, e0, e1, e2, a2, b2, c2, Q, det, out);
+    return gfp_eig_core(e0, e1, e2, a2, b2, c2, Q, det, out);
 }
 
 /*

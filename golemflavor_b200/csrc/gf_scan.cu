@@ -17,13 +17,18 @@
 
 extern std::atomic<unsigned long long> g_gf_launches;
 
+#ifndef GF_SCAN_THREADS
 #define GF_SCAN_THREADS 256
+#endif
+#ifndef GF_SCAN_MIN_BLOCKS
+#define GF_SCAN_MIN_BLOCKS 2
+#endif
 
 /* ------------------------------------------------------------------ kernels */
 
 /* Source of compositions: drawn samples (SCAN) or a given array (GIVEN). */
 template <bool SCAN, bool SMEM_HIST, int SPEC>
-__global__ void __launch_bounds__(GF_SCAN_THREADS, 2) /* <= 128 registers: two 256-thread blocks (2 x 70 KB histograms) per SM */
+__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SCAN_MIN_BLOCKS) /* default <= 128 registers: two 256-thread blocks (2 x 70 KB histograms) per SM */
     k_hist(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
            const double* __restrict__ fr_in, const int nb1, const double step, unsigned long long* __restrict__ hist,
            unsigned long long* __restrict__ accepted) {
@@ -316,7 +321,7 @@ __device__ __forceinline__ void gf_lse_merge(double& m, double& s, double m2, do
 }
 
 template <int SPEC>
-__global__ void __launch_bounds__(GF_SCAN_THREADS, 2)
+__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SCAN_MIN_BLOCKS)
     k_evidence(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
                double* __restrict__ partials /*[gridDim.x][2]*/) {
     __shared__ double sh_m[GF_SCAN_THREADS / 32], sh_s[GF_SCAN_THREADS / 32];

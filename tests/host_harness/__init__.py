@@ -102,3 +102,10 @@ def ensemble(fm, pos, lnp, nsteps, nwalkers, nchains=1, nfree=None, step0=0, thi
                               thin=thin, a=a, seed=seed, chain0=chain0)
     _lib.check(load().hh_ensemble(fm.ref, C.byref(cfg), _p(pos), _p(lnp), _p(chain), _p(lchain), _p(nacc)))
     return pos, lnp, chain, lchain, nacc.astype(np.int64)
+
+
+def cubic_w(delta):
+    d = np.ascontiguousarray(delta, dtype=np.float64)
+    w = np.empty_like(d)
+    load().hh_cubic_w(_p(d), C.c_int64(d.size), _p(w))
+    return w

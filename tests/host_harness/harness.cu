@@ -26,7 +26,7 @@ extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, 
         auto get = [&](int k) { return theta[i * d.ndim + k]; };
         unsigned s = 0u;
         double f[3];
-        lnp[i] = fixed ? gf_point_lnprob<GF_SPEC_FIXED>(d, get, f, s) : gf_point_lnprob<GF_SPEC_GENERIC>(d, get, f, s);
+        lnp[i] = fixed ? gf_point_lnprob<GF_SPEC_FIXED, 2>(d, get, f, s) : gf_point_lnprob<GF_SPEC_GENERIC, 2>(d, get, f, s); /* as k_lnprob */
         if (fr) memcpy(fr + 3 * i, f, sizeof(f));
         if (st) st[i] = (uint8_t)s;
     }
@@ -84,7 +84,6 @@ extern "C" void hh_hist(const double* fr, int64_t n, int nb, unsigned long long*
 }
 
 extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, double* vec, double* x_fast /*[n][4]*/, uint8_t* fast_ok) {
-    static const double wpoly[GFP_W_POLY_N] = GFP_W_POLY_INIT;
     for (int64_t i = 0; i < n; ++i) {
         const double* h = ham + 18 * i;
         gfp_herm3 m;
@@ -92,7 +91,7 @@ extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, do
         m.ar = h[2]; m.ai = h[3]; m.br = h[4]; m.bi = h[5]; m.cr = h[10]; m.ci = h[11];
         gfp_herm3_eig_sorted(m, lam + 3 * i, vec + 18 * i);
         gfp_x4 x = {NAN, NAN, NAN, NAN};
-        fast_ok[i] = gfp_herm3_x4_fast(wpoly, m, x) ? 1 : 0;
+        fast_ok[i] = gfp_herm3_x4_fast(m, x) ? 1 : 0;
         x_fast[4 * i] = x.x00; x_fast[4 * i + 1] = x.x01; x_fast[4 * i + 2] = x.x10; x_fast[4 * i + 3] = x.x11;
     }
 }
@@ -123,4 +122,8 @@ extern "C" int hh_ensemble(const gf_model* model, const gf_ensemble_config* cfg,
                 for (int k = 0; k < cfg->nwalkers; ++k) gf_ens_store(d, A, c, k, (s + 1) / cfg->thin - 1, nstore);
     }
     return 0;
+}
+
+extern "C" void hh_cubic_w(const double* delta, int64_t n, double* w) {
+    for (int64_t i = 0; i < n; ++i) w[i] = gfp_cubic_w(delta[i]);
 }

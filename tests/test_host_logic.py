@@ -384,3 +384,15 @@ def test_cli_identifiers_match_reference_naming():
     assert cli.gen_identifier(a, 'mc_texture') == '_DIM6_SRC_1_2_0_OET' and cli.gen_identifier(a, 'mc_unitary') == '_SRC_1_2_0'
     ns = cli._parser().parse_args(['mc_texture', '--dimension', '6', '--texture', 'out', '--nwalkers', '10'])
     assert ns.texture is Texture.OUT and ns.nwalkers == 10 and ns.binning == [6e4, 1e7, 20]
+
+
+def test_harness_cubic_root_seeded_newton_is_full_precision():
+    """w = 1 - cos(acos(1 - delta)/3) from the fp32-seeded Newton iteration: relative error of a few
+    ulp over the whole range, including delta -> 0 (where the eigen-gap lives)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    delta = np.concatenate([10.0 ** np.linspace(-14, 0, 600), np.linspace(0, 1, 401)[1:]])
+    w = hh.cubic_w(delta)
+    ref = np.array([float(1 - mp.cos(mp.acos(1 - mp.mpf(float(d))) / 3)) for d in delta])
+    assert np.max(np.abs(w / ref - 1)) < 1e-15
+    assert hh.cubic_w(np.array([0.0]))[0] == 0.0 and np.isnan(hh.cubic_w(np.array([np.nan]))[0])
