@@ -172,7 +172,7 @@ def run_reference(opts):
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -314,6 +314,7 @@ def run_gpu(opts):
         sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
         cfg_info['C3_bsm_dim6_fit'] = {'walkers': 4096, 'steps': 2000, 'ndim': fn.ndim, 'seconds': sec, 'evals_per_s': 4096 * 2000 / sec,
                                        'acceptance': float(np.mean(smp3.acceptance_fraction))}
+        sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first cooperative launches, NCCL float64 path)
         sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
         cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
                                      'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
@@ -357,12 +358,32 @@ def run_gpu(opts):
             'scan': scan_info,
             'configs': cfg_info,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """The driver parses ONE JSON line from stdout, but libraries write there too (NCCL prints its
+    version banner to fd 1 on communicator creation).  Keep a private duplicate of the real stdout
+    for the result line and point fd 1 at stderr for everybody else."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=400)
