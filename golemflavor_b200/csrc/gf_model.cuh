@@ -147,7 +147,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
         wsum += wd;
     }
     /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is 1 / (S sum(width)) */
-    const double inv = 1.0 / (S * wsum);
+    const double inv = gfp_rcp(S * wsum);
     fr[0] = a0 * inv;
     fr[1] = a1 * inv;
     fr[2] = 1.0 - fr[0] - fr[1];

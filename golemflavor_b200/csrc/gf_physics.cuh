@@ -79,6 +79,17 @@ GF_HD double gfp_rsqrt(double x) {
 #endif
 }
 
+/* sqrt(x) for the mixing-angle coordinates (x in [0, 1] inside the prior box): x * rsqrt(x), one
+ * multiplication on top of the MUFU-seeded rsqrt instead of the ~12 fp64 instructions of the IEEE
+ * routine; accurate to ~1 ulp.  Zero, tiny and out-of-domain arguments take the library path
+ * (negative -> NaN like the reference's sqrt, fr.py:146-152). */
+GF_HD double gfp_sqrt01(double x) {
+#ifdef __CUDA_ARCH__
+    if (x > 1e-290 && x < 1e290) return x * gfp_rsqrt(x);
+#endif
+    return sqrt(x);
+}
+
 /* ------------------------------------------------------------------ 3x3 Hermitian */
 
 /* Hermitian matrix: real diagonal d0,d1,d2 and the upper triangle a = H01, b = H02, c = H12. */
@@ -140,30 +151,27 @@ struct gfp_x4 {
  * pair is nearer than the fast-path limit or the input is degenerate / non-finite; the caller then
  * runs the Jacobi fallback.
  */
-GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, double c2, double Q, double det, gfp_x4& out) {
-    /* Straight-line code on purpose (no early exit): the caller evaluates two energy bins back to
-     * back and the compiler interleaves their independent dependency chains -- with 16 resident warps
-     * per SM the kernels are bound by the latency of this chain, not by fp64 issue.  Degenerate or
+GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, double c2, double Q, double hdet, gfp_x4& out) {
+    /* hdet = det / 2.  Straight-line code on purpose (no early exit): the caller evaluates two energy
+     * bins back to back and the compiler interleaves their independent dependency chains -- with 16
+     * resident warps per SM the kernels are bound by the latency of this chain.  Degenerate or
      * non-finite inputs simply produce garbage that the returned flag tells the caller to discard. */
     const double rs = gfp_rsqrt(Q);
-    const double r = (0.5 * det * rs) * (rs * rs); /* cos(phi) */
-    const double delta = 1.0 - fabs(r);            /* a rounding-negative delta gives s2 < 0 and takes the fallback */
+    const double r = (hdet * rs) * (rs * rs); /* cos(phi) */
+    const double delta = 1.0 - fabs(r);       /* a rounding-negative delta gives s2 < 0 and takes the fallback */
     const double w = gfp_cubic_w(delta);
     const double s2 = w * (2.0 - w); /* sin^2(phi/3) */
     const double sq = 2.0 * Q * rs;                     /* 2 sqrt(Q) */
     const double l0 = copysign(sq - sq * w, r);         /* 2 sqrt(Q) cos(phi/3), isolated eigenvalue */
     const double half_gap = (0.8660254037844386 * sq) * (s2 * gfp_rsqrt(s2));
     const double l1 = fma(-0.5, l0, half_gap);
-    /* eigenvector-eigenvalue identity */
-    double t0 = l0 - e0, t1 = l0 - e1, t2 = l0 - e2;
-    const double n00 = fma(t1, t2, -c2), n10 = fma(t0, t2, -b2), n20 = fma(t0, t1, -a2);
-    const double p0 = n00 + n10 + n20; /* p'(l0) */
-    t0 = l1 - e0;
-    t1 = l1 - e1;
-    t2 = l1 - e2;
-    const double n01 = fma(t1, t2, -c2), n11 = fma(t0, t2, -b2), n21 = fma(t0, t1, -a2);
-    const double p1 = n01 + n11 + n21; /* p'(l1) */
-    const double q = gfp_rcp(p0 * p1);
+    /* eigenvector-eigenvalue identity |V_ai|^2 p'(l_i) = det(l_i - M_a) for rows a = 0, 1; for the
+     * trace-free cubic p'(l) = 3 (l^2 - Q): no third minor, and the operands stay register-light
+     * (a DFMA reading three distinct register pairs issues at 2/3 rate on B200) */
+    const double n00 = fma(l0 - e1, l0 - e2, -c2), n10 = fma(l0 - e0, l0 - e2, -b2);
+    const double n01 = fma(l1 - e1, l1 - e2, -c2), n11 = fma(l1 - e0, l1 - e2, -b2);
+    const double p0 = fma(l0, l0, -Q), p1 = fma(l1, l1, -Q); /* p'(l_i) / 3 */
+    const double q = gfp_rcp(3.0 * (p0 * p1));
     const double i0 = q * p1, i1 = q * p0;
     out.x00 = n00 * i0;
     out.x10 = n10 * i0;
@@ -186,7 +194,7 @@ GF_HD bool gfp_herm3_x4_fast(const gfp_herm3& h, gfp_x4& out) {
     const double aci = fma(h.ar, h.ci, h.ai * h.cr);
     const double tri = fma(acr, h.br, aci * h.bi);
     const double det = fma(2.0, tri, e0 * e1 * e2) - fma(e0, c2, fma(e1, b2, e2 * a2));
-    return gfp_eig_core(e0, e1, e2, a2, b2, c2, p2 * (1.0 / 6.0), det, out);
+    return gfp_eig_core(e0, e1, e2, a2, b2, c2, p2 * (1.0 / 6.0), 0.5 * det, out);
 }
 
 /*
@@ -200,13 +208,13 @@ GF_HD bool gfp_herm3_x4_fast(const gfp_herm3& h, gfp_x4& out) {
 struct gfp_pencil_T {
     double te[3];        /* trace-free diagonal of T                          */
     double a22, b22, c22; /* |T01|^2, |T02|^2, |T12|^2                         */
-    double q2, d3;       /* tr(T'^2)/6, det T'                                */
+    double q2, d3;       /* tr(T'^2)/6, det(T')/2                             */
 };
 struct gfp_pencil_P {
     double e[3];                 /* trace-free diagonal of H0: e_k(rho) = e[k] + rho te[k]            */
     double a2[2], b2[2], c2[2];  /* |H01|^2(rho) = a2[0] + rho (a2[1] + rho a22), ...                  */
     double q[2];                 /* Q(rho) = q[0] + rho (q[1] + rho q2)                                */
-    double d[3];                 /* det(rho) = d[0] + rho (d[1] + rho (d[2] + rho d3))                 */
+    double d[3];                 /* det(rho)/2 = d[0] + rho (d[1] + rho (d[2] + rho d3))               */
 };
 
 /* det of a trace-free Hermitian matrix given as (e0,e1,e2,a,b,c) */
@@ -240,7 +248,7 @@ GF_HD gfp_pencil_T gfp_make_pencil_T(const gfp_herm3& T) {
     t.b22 = fma(T.br, T.br, T.bi * T.bi);
     t.c22 = fma(T.cr, T.cr, T.ci * T.ci);
     t.q2 = (1.0 / 6.0) * fma(2.0, t.a22 + t.b22 + t.c22, fma(t.te[0], t.te[0], fma(t.te[1], t.te[1], t.te[2] * t.te[2])));
-    t.d3 = gfp_det_tf(t.te, T);
+    t.d3 = 0.5 * gfp_det_tf(t.te, T);
     return t;
 }
 
@@ -254,9 +262,9 @@ GF_HD gfp_pencil_P gfp_make_pencil_P(const gfp_herm3& h0, const gfp_herm3& T, co
     const double sixth = 1.0 / 6.0;
     p.q[0] = sixth * fma(2.0, p.a2[0] + p.b2[0] + p.c2[0], fma(p.e[0], p.e[0], fma(p.e[1], p.e[1], p.e[2] * p.e[2])));
     p.q[1] = sixth * fma(2.0, p.a2[1] + p.b2[1] + p.c2[1], 2.0 * fma(p.e[0], te[0], fma(p.e[1], te[1], p.e[2] * te[2])));
-    p.d[0] = gfp_det_tf(p.e, h0);
-    p.d[1] = gfp_tr_adj(p.e, h0, te, T);
-    p.d[2] = gfp_tr_adj(te, T, p.e, h0);
+    p.d[0] = 0.5 * gfp_det_tf(p.e, h0);
+    p.d[1] = 0.5 * gfp_tr_adj(p.e, h0, te, T);
+    p.d[2] = 0.5 * gfp_tr_adj(te, T, p.e, h0);
     return p;
 }
 
@@ -266,8 +274,8 @@ GF_HD bool gfp_pencil_x4_fast(const gfp_pencil_P& p, const gfp_pencil_T& t, doub
     const double b2 = fma(fma(t.b22, rho, p.b2[1]), rho, p.b2[0]);
     const double c2 = fma(fma(t.c22, rho, p.c2[1]), rho, p.c2[0]);
     const double Q = fma(fma(t.q2, rho, p.q[1]), rho, p.q[0]);
-    const double det = fma(fma(fma(t.d3, rho, p.d[2]), rho, p.d[1]), rho, p.d[0]);
-    return gfp_eig_core(e0, e1, e2, a2, b2, c2, Q, det, out);
+    const double hdet = fma(fma(fma(t.d3, rho, p.d[2]), rho, p.d[1]), rho, p.d[0]);
+    return gfp_eig_core(e0, e1, e2, a2, b2, c2, Q, hdet, out);
 }
 
 /*
@@ -385,13 +393,13 @@ struct gfp_trig {
 
 GF_HD gfp_trig gfp_angles_trig(double s12_2, double c13_4, double s23_2, double dcp) {
     gfp_trig t;
-    t.s12 = sqrt(s12_2);
-    t.c12 = sqrt(1.0 - s12_2);
-    const double c13_2 = sqrt(c13_4);
-    t.c13 = sqrt(c13_2);
-    t.s13 = sqrt(1.0 - c13_2);
-    t.s23 = sqrt(s23_2);
-    t.c23 = sqrt(1.0 - s23_2);
+    t.s12 = gfp_sqrt01(s12_2);
+    t.c12 = gfp_sqrt01(1.0 - s12_2);
+    const double c13_2 = gfp_sqrt01(c13_4);
+    t.c13 = gfp_sqrt01(c13_2);
+    t.s13 = gfp_sqrt01(1.0 - c13_2);
+    t.s23 = gfp_sqrt01(s23_2);
+    t.c23 = gfp_sqrt01(1.0 - s23_2);
 #ifdef __CUDA_ARCH__
     sincos(dcp, &t.sd, &t.cd);
 #else
