@@ -302,6 +302,25 @@ def run_gpu(opts):
         np.random.seed(25)
         p0 = mcmc.flat_seed(ps2, 1024)
         p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
+        # K1: the SM-only log-posterior (161 algorithmic FLOP / 56 B per point) is HBM-bound: report it against HBM
+        n1 = 1 << 24
+        th1 = torch.as_tensor(_m.draw_in_ranges(ps2, 1 << 20, np.random.default_rng(3))).cuda().repeat(16, 1)
+        o1 = torch.empty(n1, dtype=torch.float64, device='cuda')
+        k1 = lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(th1), n1, 6, 1, _lib.ptr(o1), None, None, stream))
+        for _ in range(3):
+            k1()
+        torch.cuda.synchronize()
+        k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0e.record()
+        for _ in range(20):
+            k1()
+        k1e.record()
+        torch.cuda.synchronize()
+        k1ms = k0e.elapsed_time(k1e) / 20
+        cfg_info['K1_sm_lnprob'] = {'points': n1, 'ms': k1ms, 'evals_per_s': n1 / (k1ms * 1e-3), 'bound': 'hbm',
+                                    'achieved_gbs': 56.0 * n1 / (k1ms * 1e-3) / 1e9,
+                                    'note': '6-D notebook model (4 PMNS coords + 2 source angles), theta 805 MB > L2'}
+        del th1, o1
         smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
         smp.run_mcmc(p0, 200, store=False)
         sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))

@@ -32,7 +32,7 @@ extern std::atomic<unsigned long long> g_gf_launches;
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 
 template <int KIND, int SPEC>
-__global__ void __launch_bounds__(GF_LP_THREADS, GF_LP_MIN_BLOCKS)
+__global__ void __launch_bounds__(GF_LP_THREADS, SPEC == GF_SPEC_SM ? 16 : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,10 +75,14 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
     if (int rc = check_view(fn, model, d_theta, n, ld_point, ld_dim)) return rc;
     if (n == 0) return GF_OK;
     const gf_theta_view th{d_theta, ld_point, ld_dim};
-    if (KIND != GF_K_LNPRIOR && gf_model_is_fixed_spec(d))
-        k_lnprob<KIND, GF_SPEC_FIXED><<<gf_blocks_for(n, GF_LP_THREADS), GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    const int spec = KIND == GF_K_LNPRIOR ? GF_SPEC_GENERIC : gf_model_spec(d);
+    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS);
+    if (spec == GF_SPEC_FIXED)
+        k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    else if (spec == GF_SPEC_SM)
+        k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else
-        k_lnprob<KIND, GF_SPEC_GENERIC><<<gf_blocks_for(n, GF_LP_THREADS), GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+        k_lnprob<KIND, GF_SPEC_GENERIC><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     ++g_gf_launches;
     GF_LAUNCH_CHECK(fn);
     return GF_OK;
@@ -207,8 +211,12 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
         }
         GF_CUDA(cudaMemcpyAsync(p.d_theta[s], src, cnt * ndim * sizeof(double), cudaMemcpyHostToDevice, p.stream[s]));
         const gf_theta_view th{p.d_theta[s], ndim, 1};
-        if (gf_model_is_fixed_spec(d))
+        const int spec = gf_model_spec(d);
+        if (spec == GF_SPEC_FIXED)
             k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
+                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        else if (spec == GF_SPEC_SM)
+            k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else
             k_lnprob<GF_K_LNPROB, GF_SPEC_GENERIC><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(

@@ -46,6 +46,8 @@ struct gf_point {
 /*
  * Kernel specialisations (compile-time, chosen by the host from the model):
  *   GF_SPEC_GENERIC : every model; which quantities are sampled is decided by uniform branches.
+ *   GF_SPEC_SM      : models without the BSM path (m.no_bsm); the kernel then carries none of the
+ *                     eigen-stage code or registers and runs at full occupancy (HBM / latency bound).
  *   GF_SPEC_FIXED   : the production BSM shape -- fixed texture AND fixed source composition
  *                     (scripts/fr.py, mc_texture.py).  The texture part of the pencil and the
  *                     source constants are then read from the constant bank as direct DFMA operands:
@@ -53,21 +55,25 @@ struct gf_point {
  */
 #define GF_SPEC_GENERIC 0
 #define GF_SPEC_FIXED 1
+#define GF_SPEC_SM 2 /* no_bsm models (notebook SM fit, unitary / x scans): no BSM code, light on registers */
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
+GF_HD int gf_model_spec(const gf_dev_model& m);
 
 /* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
 template <int SPEC = GF_SPEC_GENERIC, class Get>
 GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
+    if (SPEC != GF_SPEC_SM) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
-    if (SPEC != GF_SPEC_FIXED && m.np_free) {
+        for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
+    }
+    if (SPEC == GF_SPEC_GENERIC && m.np_free) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
-    q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
+    if (SPEC != GF_SPEC_SM) q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
     if (SPEC == GF_SPEC_FIXED) return; /* source and NP mixing come from the constant bank */
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
@@ -158,7 +164,7 @@ template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
     unsigned st = 0u;
     const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
-    if (SPEC != GF_SPEC_FIXED && m.no_bsm) {
+    if (SPEC == GF_SPEC_SM || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
         double X[9];
         gfp_pmns_abs2(t, X);
         double f[3];
@@ -167,7 +173,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         fr[0] = f[0] * inv;
         fr[1] = f[1] * inv;
         fr[2] = f[2] * inv;
-    } else {
+    } else if (SPEC != GF_SPEC_SM) {
         const gfp_cols12 u = gfp_cols_from_trig(t);
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
          * the polynomial invariants of the pencil H0 + rho T */
@@ -205,6 +211,11 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) {
     return !m.no_bsm && !m.np_free && m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0;
+}
+
+/* which specialisation the host launches for a model */
+GF_HD int gf_model_spec(const gf_dev_model& m) {
+    return m.no_bsm ? GF_SPEC_SM : gf_model_is_fixed_spec(m) ? GF_SPEC_FIXED : GF_SPEC_GENERIC;
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside. */

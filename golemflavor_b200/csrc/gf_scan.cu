@@ -28,7 +28,7 @@ extern std::atomic<unsigned long long> g_gf_launches;
 
 /* Source of compositions: drawn samples (SCAN) or a given array (GIVEN). */
 template <bool SCAN, bool SMEM_HIST, int SPEC>
-__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SCAN_MIN_BLOCKS) /* default <= 128 registers: two 256-thread blocks (2 x 70 KB histograms) per SM */
+__global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_SCAN_MIN_BLOCKS) /* BSM: <= 128 registers, two 256-thread blocks (2 x 70 KB histograms) per SM; SM-only: three */
     k_hist(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
            const double* __restrict__ fr_in, const int nb1, const double step, unsigned long long* __restrict__ hist,
            unsigned long long* __restrict__ accepted) {
@@ -120,9 +120,9 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     const bool use_smem = smem <= kSmemHistLimit;
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
-    const bool fixed = SCAN && gf_model_is_fixed_spec(d);
-    auto kern_s = fixed ? k_hist<SCAN, true, GF_SPEC_FIXED> : k_hist<SCAN, true, GF_SPEC_GENERIC>;
-    auto kern_g = fixed ? k_hist<SCAN, false, GF_SPEC_FIXED> : k_hist<SCAN, false, GF_SPEC_GENERIC>;
+    const int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
+    auto kern_s = spec == GF_SPEC_FIXED ? k_hist<SCAN, true, GF_SPEC_FIXED> : spec == GF_SPEC_SM ? k_hist<SCAN, true, GF_SPEC_SM> : k_hist<SCAN, true, GF_SPEC_GENERIC>;
+    auto kern_g = spec == GF_SPEC_FIXED ? k_hist<SCAN, false, GF_SPEC_FIXED> : spec == GF_SPEC_SM ? k_hist<SCAN, false, GF_SPEC_SM> : k_hist<SCAN, false, GF_SPEC_GENERIC>;
     int per_sm = 1;
     if (use_smem) {
         GF_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
