@@ -163,10 +163,9 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
     unsigned st = 0u;
-    const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
     if (SPEC == GF_SPEC_SM || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
         double X[9];
-        gfp_pmns_abs2(t, X);
+        gfp_pmns_abs2_coords(q.sm[0], q.sm[1], q.sm[2], q.sm[3], X);
         double f[3];
         gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
         const double inv = 1.0 / (q.src[0] + q.src[1] + q.src[2]);
@@ -174,6 +173,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         fr[1] = f[1] * inv;
         fr[2] = f[2] * inv;
     } else if (SPEC != GF_SPEC_SM) {
+        const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
         const gfp_cols12 u = gfp_cols_from_trig(t);
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
          * the polynomial invariants of the pencil H0 + rho T */

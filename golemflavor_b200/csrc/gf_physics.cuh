@@ -456,6 +456,28 @@ GF_HD void gfp_pmns_abs2(const gfp_trig& t, double* X) {
     X[8] = c23_2 * c13_2;
 }
 
+/* |U_ai|^2 straight from the Haar-flat coordinates (s12^2, c13^4, s23^2, dcp): the squared sines and
+ * cosines ARE the coordinates (fr.py:146-155 round-trips them through asin / sin), so the SM-only
+ * models need two square roots -- c13^2 = sqrt(c13^4) and the interference term -- and cos(dcp) only. */
+GF_HD void gfp_pmns_abs2_coords(double s12_2, double c13_4, double s23_2, double dcp, double* X) {
+    const double c12_2 = 1.0 - s12_2, c23_2 = 1.0 - s23_2;
+    const double c13_2 = gfp_sqrt01(c13_4), s13_2 = 1.0 - c13_2;
+    /* 2 c23 s23 s12 c12 s13 cos(dcp); every factor is a non-negative root inside the prior box, a
+     * negative coordinate makes the product's root NaN exactly where the reference's sqrt is NaN */
+    const bool valid = s12_2 >= 0.0 && c12_2 >= 0.0 && s23_2 >= 0.0 && c23_2 >= 0.0 && s13_2 >= 0.0;
+    const double prod = (c23_2 * s23_2) * (s12_2 * c12_2) * s13_2;
+    const double cross = valid ? 2.0 * gfp_sqrt01(prod) * cos(dcp) : NAN;
+    X[0] = c13_2 * c12_2;
+    X[1] = c13_2 * s12_2;
+    X[2] = s13_2;
+    X[3] = fma(c23_2, s12_2, s23_2 * s13_2 * c12_2) + cross;
+    X[4] = fma(c23_2, c12_2, s23_2 * s13_2 * s12_2) - cross;
+    X[5] = s23_2 * c13_2;
+    X[6] = fma(s23_2, s12_2, c23_2 * s13_2 * c12_2) - cross;
+    X[7] = fma(s23_2, c12_2, c23_2 * s13_2 * s12_2) + cross;
+    X[8] = c23_2 * c13_2;
+}
+
 /* H = m1 u1 u1^+ + m2 u2 u2^+ for the columns above (U diag(0,m1,m2) U^+, fr.py:383-394). */
 GF_HD gfp_herm3 gfp_herm_from_cols(const gfp_cols12& u, double m1, double m2) {
     gfp_herm3 h;
