@@ -187,6 +187,14 @@ def run_gpu(opts):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
+    try:  # keep this rank (and the pinned buffers it first-touches) on the CPUs / NUMA node next to its GPU
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        phys = int(visible.split(',')[local]) if visible and visible.split(',')[local].isdigit() else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:  # noqa: BLE001  (affinity is an optimisation, never a requirement)
+        pass
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     lib = _lib.load()
