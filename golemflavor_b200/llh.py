@@ -113,16 +113,20 @@ class LnProb(object):
         res = (out,) + ((fr,) if want_fr else ()) + ((st,) if want_status else ())
         return res if len(res) > 1 else out
 
-    def evaluate_host(self, theta, out=None):
+    def evaluate_host(self, theta, out=None, fr=None, status=None):
         """theta [N, ndim] float64 NumPy (ideally page-locked) -> lnprob [N] NumPy, through the
-        chunked H2D / kernel / D2H pipeline of ``gf_lnprob_host``."""
+        chunked H2D / kernel / D2H pipeline of ``gf_lnprob_host``.  Optional output arrays
+        ``fr`` [N, 3] float64 and ``status`` [N] uint8 are filled when given."""
         _lib.torch_cuda()
         th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, self.ndim)
         n = th.shape[0]
         if out is None:
             out = np.empty((n,), dtype=np.float64)
-        _lib.check(_lib.load().gf_lnprob_host(self.model.ref, th.ctypes.data_as(C.c_void_p), n,
-                                              out.ctypes.data_as(C.c_void_p), None, None))
+        for name, arr, shape, dt in (('out', out, (n,), np.float64), ('fr', fr, (n, 3), np.float64), ('status', status, (n,), np.uint8)):
+            if arr is not None and (arr.shape != shape or arr.dtype != dt or not arr.flags['C_CONTIGUOUS']):
+                raise ValueError('{0} must be a C-contiguous {1} array of shape {2}'.format(name, np.dtype(dt).name, shape))
+        ptr = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(_lib.load().gf_lnprob_host(self.model.ref, ptr(th), n, ptr(out), ptr(fr), ptr(status)))
         return out
 
     def __call__(self, theta):

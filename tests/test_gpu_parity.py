@@ -599,3 +599,42 @@ def test_cli_scan_outputs(torch, tmp_path):
     assert np.abs(arr[:, :3] - ref).max() < FR_TOL
     out = cli.main(['fr', '--dimension', '6', '--texture', 'OET', '--nwalkers', '32', '--burnin', '20', '--nsteps', '30', '--datadir', str(tmp_path)])
     assert out.endswith('chain_DIM6_sfr_1_2_0_mfr_1_1_1_OET.npy') and np.load(out).shape == (32 * 30, 7)
+
+
+def test_reference_call_variants(torch, golden):
+    """Argument forms of the reference API: texture enums, no_bsm, tensors in / tensors out, host outputs."""
+    g = golden('ref_bsm_u.npz')
+    k = int(np.where(g['tex'] == 'OET')[0][0])
+    smu = fr.angles_to_u(g['sm'][k])
+    # texture given as enum + scalar scale == Texture.NONE with the explicit angle tuple (fr.py:367-378)
+    v1 = fr.params_to_BSMu(g['loglam'][k], int(g['dim'][k]), g['energy'][k], mass_eigenvalues=g['mass'][k], sm_u=smu, texture=Texture.OET)
+    v2 = fr.params_to_BSMu(tuple(model.TEXTURE_ANGLES['OET']) + (g['loglam'][k],), int(g['dim'][k]), g['energy'][k],
+                           mass_eigenvalues=g['mass'][k], sm_u=smu)
+    assert np.array_equal(v1, v2) and v1.shape == (3, 3)
+    # no_bsm: eigenvectors of U diag(0, m21, m3x) U^+ are U's columns (ascending eigenvalue) up to phases
+    v0 = fr.params_to_BSMu((0, 0, 0, 0, -30), 6, 1e5, sm_u=smu, no_bsm=True)
+    assert np.abs(np.abs(v0) ** 2 - np.abs(smu) ** 2).max() < 1e-12
+    assert np.abs(fr.u_to_fr((1, 2, 0), v0) - fr.u_to_fr((1, 2, 0), smu)).max() < 1e-13
+    with pytest.raises(ValueError):
+        fr.params_to_BSMu((0.1, 0.2, 0.3), 6, 1e5)          # Texture.NONE needs 5 entries
+    with pytest.raises(ValueError):
+        fr.params_to_BSMu((0, 0, 0, 0, -30), 6, 1e5, sm_u=np.eye(2))
+    # tensors in -> tensors out, nothing leaves the device
+    ang = torch.as_tensor(g['sm']).cuda()
+    u = fr.angles_to_u(ang)
+    assert u.is_cuda and u.dtype == torch.complex128 and u.shape == (len(g['sm']), 3, 3)
+    f = fr.u_to_fr(torch.tensor([1., 2., 0.], device='cuda'), u)
+    assert f.is_cuda and np.abs(f.cpu().numpy() - fr.u_to_fr((1, 2, 0), u.cpu().numpy())).max() == 0
+    # host pipeline with the optional outputs
+    gl = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(gl['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    th = models.draw_in_ranges(pset, 70000, np.random.default_rng(5))
+    th[::13, 1] = 1.5
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(th, want_fr=True, want_status=True))
+    h_fr, h_st = np.empty((70000, 3)), np.empty(70000, dtype=np.uint8)
+    h_lnp = fn.evaluate_host(th, fr=h_fr, status=h_st)
+    assert np.array_equal(h_lnp, lnp) and np.array_equal(h_st, st) and np.array_equal(np.isnan(h_fr), np.isnan(frs))
+    assert np.array_equal(h_fr[~np.isnan(h_fr)], frs[~np.isnan(frs)])
+    with pytest.raises(ValueError):
+        fn.evaluate_host(th, fr=np.empty((5, 3)))
