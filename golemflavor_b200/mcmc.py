@@ -165,7 +165,8 @@ class EnsembleSampler(object):
 class DeviceEnsembleSampler(object):
     """Device-resident stretch-move sampler (C ABI ``gf_ensemble_run``): proposal, log-posterior and
     accept/reject of every half-step run inside one kernel, for ``nchains`` independent ensembles at
-    once; the whole ``run_mcmc`` call is a single cooperative launch when the batch is co-resident.
+    once; the whole ``run_mcmc`` call is a single launch (one block per chain for ensembles of up to
+    512 walkers, a cooperative grid otherwise).
 
     Same emcee-2 surface as ``EnsembleSampler`` (``chain``, ``lnprobability``, ``acceptance_fraction``,
     ``acor``, ``flatchain``, ``reset``, ``run_mcmc``, ``sample``); with ``nchains > 1`` the arrays gain
@@ -173,7 +174,7 @@ class DeviceEnsembleSampler(object):
     identical in all walkers of a chain stay frozen; pass ``nfree`` = number of sampled dimensions.
     """
 
-    def __init__(self, nwalkers, ndim, lnprob, nchains=1, a=2.0, seed=0, nfree=None, store_lnprob=True, chain0=0):
+    def __init__(self, nwalkers, ndim, lnprob, nchains=1, a=2.0, seed=0, nfree=None, store_lnprob=True, chain0=0, mode=0):
         from . import _lib
         if nwalkers % 2 != 0:
             raise ValueError('The number of walkers must be even.')
@@ -185,6 +186,7 @@ class DeviceEnsembleSampler(object):
         if self.k < 2 * self.nfree:
             raise ValueError('The number of walkers needs to be more than twice the dimension of your parameter space.')
         self.lnprob, self.seed, self.store_lnprob, self.chain0 = lnprob, int(seed), bool(store_lnprob), int(chain0)
+        self.mode = int(mode)   # 0 auto, 1 grid barrier, 2 block per chain (gf_ensemble_config.mode)
         self.total_steps = 0   # global step counter = RNG counter offset: continuing a run never reuses draws
         self._last = None
         self.reset()
@@ -251,7 +253,7 @@ class DeviceEnsembleSampler(object):
         if self._naccept is None:
             self._naccept = torch.zeros((self.nchains, self.k), dtype=torch.int64, device='cuda')
         cfg = _lib.EnsembleConfig(nchains=self.nchains, nwalkers=self.k, nfree=self.nfree, nsteps=int(N),
-                                  step0=self.total_steps, thin=int(thin), a=self.a, seed=self.seed, chain0=self.chain0)
+                                  step0=self.total_steps, thin=int(thin), a=self.a, seed=self.seed, chain0=self.chain0, mode=self.mode)
         _lib.check(_lib.load().gf_ensemble_run(self.lnprob.model.ref, C.byref(cfg), _lib.ptr(pos), _lib.ptr(lnp),
                                                _lib.ptr(chain), _lib.ptr(lchain), _lib.ptr(self._naccept),
                                                _lib.stream_ptr(torch)))

@@ -216,8 +216,10 @@ int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells, double cov
  * Device-resident affine-invariant ensemble sampler: the stretch move of emcee's EnsembleSampler
  * (Goodman & Weare 2010; red/blue half-ensembles, parameter a) that golemflavor/mcmc.py:27-53 drives
  * from Python, for `nchains` INDEPENDENT ensembles of `nwalkers` walkers at once (one thread per
- * walker pair; the whole run is one cooperative launch with a grid barrier per half-step when the
- * batch is co-resident, one launch per half-step otherwise).
+ * walker pair; ensembles whose half fits one thread block -- up to 512 walkers -- live in one block per
+ * chain with block-level barriers; larger ones run as one cooperative launch with a grid barrier per
+ * half-step when the batch is co-resident, one launch per half-step otherwise; all three shapes give
+ * identical chains).
  *
  * Randomness (reproducible on the CPU, see tests): walker k of chain c at global step s uses
  * Philox4x32-10 with key = (lo32(seed), hi32(seed)), counter = ((chain0 + c)*nwalkers + k, lo32(s), hi32(s), 0)
@@ -239,6 +241,9 @@ typedef struct gf_ensemble_config {
     double a;            /* stretch scale (emcee default 2.0)                       */
     uint64_t seed;
     int64_t chain0;      /* global index of the first chain (RNG counter offset)    */
+    int32_t mode;        /* 0 = auto; 1 = grid-wide barrier per half-step (one cooperative launch, or one
+                            launch per half-step when not co-resident); 2 = one block per chain        */
+    int32_t reserved;
 } gf_ensemble_config;
 /* d_pos [nchains][nwalkers][ndim] and d_lnp [nchains][nwalkers] are updated in place (d_lnp must hold
  * ln_prob(d_pos) on entry: call gf_lnprob first).  Optional outputs: d_chain

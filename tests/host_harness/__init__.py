@@ -99,7 +99,7 @@ def ensemble(fm, pos, lnp, nsteps, nwalkers, nchains=1, nfree=None, step0=0, thi
     lchain = np.zeros((nchains, nwalkers, nstore))
     nacc = np.zeros((nchains, nwalkers), dtype=np.uint64)
     cfg = _lib.EnsembleConfig(nchains=nchains, nwalkers=nwalkers, nfree=nfree or ndim, nsteps=nsteps, step0=step0,
-                              thin=thin, a=a, seed=seed, chain0=chain0)
+                              thin=thin, a=a, seed=seed, chain0=chain0, mode=0)
     _lib.check(load().hh_ensemble(fm.ref, C.byref(cfg), _p(pos), _p(lnp), _p(chain), _p(lchain), _p(nacc)))
     return pos, lnp, chain, lchain, nacc.astype(np.int64)
 

@@ -460,7 +460,7 @@ def test_device_sampler_replays_numpy_stretch_move(torch, golden):
     lib = _lib.load()
     before = lib.gf_launch_count()
     pos, lnp, _ = s.run_mcmc(p0, 120)
-    assert lib.gf_launch_count() - before == 2           # initial scoring + ONE cooperative launch
+    assert lib.gf_launch_count() - before == 2           # initial scoring + ONE launch for the whole chain
     rp, rl, rchain, racc = ref_sampler.run(lambda q: fn(q), p0, l0, 120, seed=5)
     same = np.mean(s.chain == rchain)
     assert same > 0.999, same
@@ -474,8 +474,9 @@ def test_device_sampler_replays_numpy_stretch_move(torch, golden):
 
 
 def test_device_sampler_many_chains_and_launch_paths(torch, golden):
-    """Batched independent chains: a co-resident batch (one cooperative launch) and a batch too large
-    for co-residency (one launch per half-step) must give the same chains."""
+    """Batched independent chains through the three launch shapes -- one block per chain, one
+    cooperative grid launch, one launch per half-step (batch too large for co-residency) -- must give
+    identical chains, and a sub-set of chains must not depend on what else is in the batch."""
     g = golden('ref_llh.npz')
     args, asimov, pset = models.notebook_model(g['asimov_angles'])
     fn = llh.LnProb(args, asimov, pset)
@@ -484,15 +485,31 @@ def test_device_sampler_many_chains_and_launch_paths(torch, golden):
     p0 = models.draw_in_ranges(pset, k * nchains, rng, seeds=True).reshape(nchains, k, 6)
     p0[:, :, 4], p0[:, :, 5] = rng.uniform(.9, 1, (nchains, k)), rng.uniform(.8, 1, (nchains, k))
     lib = _lib.load()
-    big = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3)
+    big = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3, mode=1)    # grid barrier; not co-resident
     before = lib.gf_launch_count()
     big.run_mcmc(p0, nsteps)
     assert lib.gf_launch_count() - before == 1 + 3 * nsteps     # scoring + (2 half-steps + 1 store) per step
+    blk = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3)            # auto: one block per chain
+    before = lib.gf_launch_count()
+    blk.run_mcmc(p0, nsteps)
+    assert lib.gf_launch_count() - before == 2                  # scoring + ONE launch
+    assert np.array_equal(blk.chain, big.chain) and np.array_equal(blk.acceptance_fraction, big.acceptance_fraction)
     sub = slice(4100, 4110)
-    small = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=10, seed=3, chain0=4100)
-    small.run_mcmc(p0[sub], nsteps)
-    assert np.array_equal(big.chain[sub], small.chain)
+    coop = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=10, seed=3, chain0=4100, mode=1)   # co-resident: cooperative launch
+    before = lib.gf_launch_count()
+    coop.run_mcmc(p0[sub], nsteps)
+    assert lib.gf_launch_count() - before == 2
+    assert np.array_equal(big.chain[sub], coop.chain)
     assert big.chain.shape == (nchains, k, nsteps, 6) and big.acceptance_fraction.shape == (nchains, k)
+    # block mode with several walker pairs per thread (2 x 300 > 256 threads) and a large ensemble (grid path)
+    for kk in (600, 4096):
+        q0 = models.draw_in_ranges(pset, kk, rng, seeds=True)
+        q0[:, 4], q0[:, 5] = rng.uniform(.9, 1, kk), rng.uniform(.8, 1, kk)
+        a = mcmc.DeviceEnsembleSampler(kk, 6, fn, seed=8, mode=2 if kk == 600 else 0)
+        b = mcmc.DeviceEnsembleSampler(kk, 6, fn, seed=8, mode=1)
+        a.run_mcmc(q0, 5)
+        b.run_mcmc(q0, 5)
+        assert np.array_equal(a.chain, b.chain)
 
 
 def test_mcmc_driver_uses_device_sampler_and_recovers_injection(torch, golden, capsys):
