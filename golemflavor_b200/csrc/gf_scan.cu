@@ -20,6 +20,11 @@ extern std::atomic<unsigned long long> g_gf_launches;
 #ifndef GF_SCAN_THREADS
 #define GF_SCAN_THREADS 256
 #endif
+/* bins interleaved per thread in the scan kernels (see gf_bin_loop): 1 -- with the draw state on top
+ * of the physics a second chain spills at 128 registers (A/B: 4.69e9 vs 4.78e9 samples/s) */
+#ifndef GF_SCAN_ILP
+#define GF_SCAN_ILP 1
+#endif
 #ifndef GF_SCAN_MIN_BLOCKS
 #define GF_SCAN_MIN_BLOCKS 2
 #endif
@@ -47,7 +52,7 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_S
             gf_draw_theta(m, seed, first_index + j, theta);
             gf_point q;
             gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
-            gf_point_fr<SPEC>(m, q, fr);
+            gf_point_fr<SPEC, GF_SCAN_ILP>(m, q, fr);
         } else {
             fr[0] = fr_in[3 * j];
             fr[1] = fr_in[3 * j + 1];
