@@ -32,29 +32,35 @@ GF_HD gf_u4 gf_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 
 GF_HD double gf_u01(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
 
+/* The inverse normal CDF is a large routine (rational approximations with dozens of fp64 immediates):
+ * keep ONE out-of-line copy per kernel instead of one per unrolled parameter slot -- the scan kernels
+ * were 88 KB of code with 83 % instruction-cache hit rate before. */
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ double gf_normcdfinv(double p) { return normcdfinv(p); }
+#else
+inline double gf_normcdfinv(double p) { return NAN * p; } /* evaluated on the device only */
+#endif
+
 /* Draw parameter k of sample `index` from its prior (see gf_scan_config in the C header). */
 GF_HD double gf_draw_dim(const gf_dev_model& m, int k, double u) {
     if (m.kind[k] == GF_PRIOR_UNIFORM) return fma(u, m.hi[k] - m.lo[k], m.lo[k]);
     const double p = fma(u, m.cdf_span[k], m.cdf_lo[k]);
-#ifdef __CUDA_ARCH__
-    const double x = fma(m.sigma[k], normcdfinv(p), m.mu[k]);
-#else
-    const double x = NAN * p; /* the inverse normal CDF is evaluated on the device only */
-#endif
+    const double x = fma(m.sigma[k], gf_normcdfinv(p), m.mu[k]);
     return fmin(fmax(x, m.lo[k]), m.hi[k]);
 }
 
 GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, double* theta) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
-    for (int blk = 0; 4 * blk < m.ndim; ++blk) {
-        const gf_u4 r = gf_philox4x32_10(c0, c1, (uint32_t)blk, 0u, k0, k1);
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = 4 * blk + j;
-            if (k < m.ndim) theta[k] = gf_draw_dim(m, k, gf_u01(w[j]));
-        }
+    gf_u4 r = {0u, 0u, 0u, 0u};
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int k = 0; k < m.ndim; ++k) {
+        const int j = k & 3;
+        if (j == 0) r = gf_philox4x32_10(c0, c1, (uint32_t)(k >> 2), 0u, k0, k1);
+        const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
+        theta[k] = gf_draw_dim(m, k, gf_u01(w));
     }
 }
 
