@@ -171,7 +171,7 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
         const double a = (p.lo - p.mu) / p.sigma, b = (p.hi - p.mu) / p.sigma;
         const double lognorm_free = -log(p.sigma * sqrt(2.0 * M_PI));
         /* llh.py:82-85: GAUSSIAN is an unbounded normal; llh.py:86-90: LIMITEDGAUSS is truncated to ranges */
-        d->lognorm[k] = (p.kind == GF_PRIOR_GAUSSIAN) ? lognorm_free : lognorm_free - log_gauss_mass(a, b);
+        d->lognorm_total += (p.kind == GF_PRIOR_GAUSSIAN) ? lognorm_free : lognorm_free - log_gauss_mass(a, b);
         /* scans draw inside `ranges` for both kinds (the box check of llh.py:74-78 applies to both) */
         d->cdf_lo[k] = gauss_cdf(a);
         d->cdf_span[k] = gauss_cdf(b) - gauss_cdf(a);

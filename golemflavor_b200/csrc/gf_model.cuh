@@ -26,7 +26,8 @@ struct gf_dev_model {
     double half_inv_s2;         /* 1/(2 sigma^2)                                        */
     double lognorm3;            /* -1.5 log(2 pi sigma^2)                               */
     double offset, underflow_logpdf, llh_const, epsilon;
-    double lo[GF_MAX_DIM], hi[GF_MAX_DIM], mu[GF_MAX_DIM], inv_sigma[GF_MAX_DIM], lognorm[GF_MAX_DIM];
+    double lo[GF_MAX_DIM], hi[GF_MAX_DIM], mu[GF_MAX_DIM], inv_sigma[GF_MAX_DIM]; /* inv_sigma = 0: uniform */
+    double lognorm_total;       /* sum of the Gaussian dimensions' log-normalisers       */
     double cdf_lo[GF_MAX_DIM], cdf_span[GF_MAX_DIM], sigma[GF_MAX_DIM]; /* scans: inverse-CDF draws */
     int32_t kind[GF_MAX_DIM];
 };
@@ -168,7 +169,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         gfp_pmns_abs2_coords(q.sm[0], q.sm[1], q.sm[2], q.sm[3], X);
         double f[3];
         gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
-        const double inv = 1.0 / (q.src[0] + q.src[1] + q.src[2]);
+        const double inv = gfp_rcp(q.src[0] + q.src[1] + q.src[2]); /* fr.py:535 */
         fr[0] = f[0] * inv;
         fr[1] = f[1] * inv;
         fr[2] = f[2] * inv;
@@ -218,20 +219,20 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
     return m.no_bsm ? GF_SPEC_SM : gf_model_is_fixed_spec(m) ? GF_SPEC_FIXED : GF_SPEC_GENERIC;
 }
 
-/* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside. */
+/* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.
+ * Branch-free per dimension: uniform dimensions carry inv_sigma = 0 (their z vanishes) and the
+ * normalisers of all Gaussian dimensions are pre-summed on the host (m.lognorm_total). */
 template <class Get>
 GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
-    double lp = 0.0;
+    double acc = 0.0;
     bool inside = true;
     for (int k = 0; k < m.ndim; ++k) {
         const double v = get(k);
         inside = inside && (v >= m.lo[k]) && (v <= m.hi[k]);
-        if (m.kind[k] != GF_PRIOR_UNIFORM) {
-            const double z = (v - m.mu[k]) * m.inv_sigma[k];
-            lp += fma(-0.5 * z, z, m.lognorm[k]);
-        }
+        const double z = (v - m.mu[k]) * m.inv_sigma[k];
+        acc = fma(z, z, acc);
     }
-    return inside ? lp : -INFINITY;
+    return inside ? fma(-0.5, acc, m.lognorm_total) : -INFINITY;
 }
 
 /* llh.multi_gaussian (llh.py:53-54) in closed form, with the pdf-underflow -> -inf emulation. */
