@@ -133,12 +133,16 @@ int gf_build_dev_model(const gf_model* m, gf_dev_model* d) {
             const double ec = sqrt(lo * hi);                                   /* fr.py:413 */
             d->g[b] = 2.0 * pow(ec, (double)(m->dimension - 2)) * GFP_MASS_SCALE; /* 2E * E^(d-3), fr.py:386,394 */
             d->width[b] = fabs(hi - lo);                                       /* fr.py:414 */
+            d->wsum += d->width[b];
         }
+        GF_REQUIRE(d->wsum > 0.0 && isfinite(d->wsum), "model.bin_edges: the bins have no width");
+        d->inv_S_wsum = 1.0 / (d->src_S * d->wsum);
         /* fixed new-physics mixing: T = N diag(0, 1/100, 1) N^+  (fr.py:380-381, 390-394) */
         const gfp_trig tn = gfp_angles_trig(m->fixed_np[0], m->fixed_np[1], m->fixed_np[2], m->fixed_np[3]);
-        d->T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
+        d->T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
         if (!d->np_free) GF_REQUIRE(isfinite(d->T.d0 + d->T.d1 + d->T.d2), "model.fixed_np does not describe mixing angles");
         d->penT = gfp_make_pencil_T(d->T);
+        d->adjT = gfp_adj_tf(d->penT.te, d->T);
     }
 
     d->fr_bf[0] = m->fr_bf[0];

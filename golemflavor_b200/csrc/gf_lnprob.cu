@@ -75,7 +75,7 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
     if (int rc = check_view(fn, model, d_theta, n, ld_point, ld_dim)) return rc;
     if (n == 0) return GF_OK;
     const gf_theta_view th{d_theta, ld_point, ld_dim};
-    const int spec = KIND == GF_K_LNPRIOR ? GF_SPEC_GENERIC : gf_model_spec(d);
+    const int spec = KIND == GF_K_LNPRIOR ? GF_SPEC_GENERIC : gf_model_spec(d); /* NPFREE falls through to GENERIC */
     const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS);
     if (spec == GF_SPEC_FIXED)
         k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);

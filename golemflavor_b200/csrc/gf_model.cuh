@@ -19,6 +19,9 @@ struct gf_dev_model {
     double fixed_sm[4], fixed_mass[2], fixed_src[3], fixed_np[4], fixed_loglam;
     gfp_herm3 T;                /* N diag(0,.01,1) N^+ for the fixed NP angles          */
     gfp_pencil_T penT;          /* its pencil coefficients (fixed textures)              */
+    gfp_adj3 adjT;              /* adj(T'), the rho^2 coefficient of det is tr(adj(T') H0')/2 */
+    double wsum;                /* sum of the bin widths                                 */
+    double inv_S_wsum;          /* fixed source: 1 / (src_S wsum)                        */
     double src_S, src_sd0, src_sd1; /* fixed source: s0+s1+s2, s0-s2, s1-s2              */
     double g[GF_MAX_BINS];      /* 2 Ec^(dim-2) 2^70: H*2E = H0 + 10^logLam g T          */
     double width[GF_MAX_BINS];  /* |E_hi - E_lo|                          (fr.py:414)    */
@@ -57,6 +60,11 @@ struct gf_point {
 #define GF_SPEC_GENERIC 0
 #define GF_SPEC_FIXED 1
 #define GF_SPEC_SM 2 /* no_bsm models (notebook SM fit, unitary / x scans): no BSM code, light on registers */
+/*   GF_SPEC_NPFREE  : Haar-random NP mixing (4 sampled NP angles) with a FIXED source composition -- the
+ *                     anarchic scan.  The source constants come from the constant bank, which frees the
+ *                     registers the second interleaved bin chain needs.  Scan kernels only; the
+ *                     log-posterior launcher serves such models with GF_SPEC_GENERIC. */
+#define GF_SPEC_NPFREE 3
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -70,12 +78,12 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
     }
-    if (SPEC == GF_SPEC_GENERIC && m.np_free) {
+    if ((SPEC == GF_SPEC_GENERIC && m.np_free) || SPEC == GF_SPEC_NPFREE) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
     if (SPEC != GF_SPEC_SM) q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
-    if (SPEC == GF_SPEC_FIXED) return; /* source and NP mixing come from the constant bank */
+    if (SPEC == GF_SPEC_FIXED || SPEC == GF_SPEC_NPFREE) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
     } else if (m.col_src3[0] >= 0) {
@@ -106,9 +114,9 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * fallback), the transition in its four independent entries and the width-weighted sums. */
 template <int ILP, class TPART>
 GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
-                           double lam, double s2, double sd0, double sd1, double S, double* fr) {
+                           double lam, double s2, double sd0, double sd1, double inv_norm, double S, double* fr) {
     unsigned st = 0u;
-    double a0 = 0.0, a1 = 0.0, wsum = 0.0;
+    double a0 = 0.0, a1 = 0.0;
     /* ILP = 2: two bins per iteration, i.e. two independent fast-path chains in flight per thread
      * (+10 % on k_lnprob, which is bound by the latency of that chain at 16 warps per SM); kernels with
      * more per-thread state (the scans) keep ILP = 1 because the second chain would spill */
@@ -136,7 +144,6 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
         const double wd0 = m.width[b], wd1 = m.width[b + 1];
         a0 = fma(wd1, f10, fma(wd0, f00, a0));
         a1 = fma(wd1, f11, fma(wd0, f01, a1));
-        wsum += wd0 + wd1;
     }
     for (; b < m.nbins; ++b) { /* ILP = 1, or the last of an odd number of bins */
         const double rho = lam * m.g[b];
@@ -151,12 +158,10 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
         const double wd = m.width[b];
         a0 = fma(wd, f0, a0);
         a1 = fma(wd, f1, a1);
-        wsum += wd;
     }
-    /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is 1 / (S sum(width)) */
-    const double inv = gfp_rcp(S * wsum);
-    fr[0] = a0 * inv;
-    fr[1] = a1 * inv;
+    /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is inv_norm = 1 / (S sum(width)) */
+    fr[0] = a0 * inv_norm;
+    fr[1] = a1 * inv_norm;
     fr[2] = 1.0 - fr[0] - fr[1];
     return st;
 }
@@ -178,7 +183,8 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         const gfp_cols12 u = gfp_cols_from_trig(t);
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
          * the polynomial invariants of the pencil H0 + rho T */
-        gfp_herm3 h0 = gfp_herm_from_cols(u, q.mass[0] * GFP_MASS_SCALE, q.mass[1] * GFP_MASS_SCALE);
+        const double m1 = q.mass[0] * GFP_MASS_SCALE, m2 = q.mass[1] * GFP_MASS_SCALE;
+        gfp_herm3 h0 = gfp_herm_from_cols(u, m1, m2);
 #ifdef __CUDA_ARCH__
         const double lam = exp10(q.loglam);
 #else
@@ -186,20 +192,24 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
 #endif
         if (SPEC == GF_SPEC_FIXED) {
             gfp_herm3 T = m.T;
-            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m.T, m.penT.te);
-            st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.src_S, fr);
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
+            st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
         } else {
             gfp_herm3 T;
-            if (m.np_free) {
+            if (SPEC == GF_SPEC_NPFREE || m.np_free) {
                 const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
-                T = gfp_herm_from_cols(gfp_cols_from_trig(tn), 0.01, 1.0);
+                T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
             } else {
                 T = m.T;
             }
             const gfp_pencil_T pt = gfp_make_pencil_T(T);
-            const gfp_pencil_P pp = gfp_make_pencil_P(h0, T, pt.te);
-            st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2],
-                             q.src[0] + q.src[1] + q.src[2], fr);
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, (SPEC == GF_SPEC_NPFREE || m.np_free) ? gfp_adj_tf(pt.te, T) : m.adjT);
+            if (SPEC == GF_SPEC_NPFREE) {
+                st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            } else {
+                const double S = q.src[0] + q.src[1] + q.src[2];
+                st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], gfp_rcp(S * m.wsum), S, fr);
+            }
         }
         /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
          * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
@@ -210,13 +220,16 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
     return st;
 }
 
-GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) {
-    return !m.no_bsm && !m.np_free && m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0;
-}
+GF_HD bool gf_model_has_fixed_source(const gf_dev_model& m) { return m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0; }
 
-/* which specialisation the host launches for a model */
+GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) { return !m.no_bsm && !m.np_free && gf_model_has_fixed_source(m); }
+
+/* which specialisation the host launches for a model (kernels without a GF_SPEC_NPFREE instance map it
+ * to GF_SPEC_GENERIC) */
 GF_HD int gf_model_spec(const gf_dev_model& m) {
-    return m.no_bsm ? GF_SPEC_SM : gf_model_is_fixed_spec(m) ? GF_SPEC_FIXED : GF_SPEC_GENERIC;
+    if (m.no_bsm) return GF_SPEC_SM;
+    if (!gf_model_has_fixed_source(m)) return GF_SPEC_GENERIC;
+    return m.np_free ? GF_SPEC_NPFREE : GF_SPEC_FIXED;
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.

@@ -217,28 +217,47 @@ struct gfp_pencil_P {
     double d[3];                 /* det(rho)/2 = d[0] + rho (d[1] + rho (d[2] + rho d3))               */
 };
 
-/* det of a trace-free Hermitian matrix given as (e0,e1,e2,a,b,c) */
-GF_HD double gfp_det_tf(const double* e, const gfp_herm3& h) {
-    const double a2 = fma(h.ar, h.ar, h.ai * h.ai), b2 = fma(h.br, h.br, h.bi * h.bi), c2 = fma(h.cr, h.cr, h.ci * h.ci);
-    const double acr = fma(h.ar, h.cr, -(h.ai * h.ci)), aci = fma(h.ar, h.ci, h.ai * h.cr);
-    const double tri = fma(acr, h.br, aci * h.bi);
-    return fma(2.0, tri, e[0] * e[1] * e[2]) - fma(e[0], c2, fma(e[1], b2, e[2] * a2));
+/* Adjugate of a trace-free Hermitian matrix A = (ea, A.offdiag): real diagonal cofactors k and the
+ * upper triangle j01, j02, j12.  For the fixed textures adj(T') is a model constant (host). */
+struct gfp_adj3 {
+    double k0, k1, k2;
+    double j01r, j01i, j02r, j02i, j12r, j12i;
+};
+
+GF_HD gfp_adj3 gfp_adj_tf(const double* ea, const gfp_herm3& A) {
+    gfp_adj3 j;
+    const double a2 = fma(A.ar, A.ar, A.ai * A.ai), b2 = fma(A.br, A.br, A.bi * A.bi), c2 = fma(A.cr, A.cr, A.ci * A.ci);
+    j.k0 = fma(ea[1], ea[2], -c2); j.k1 = fma(ea[0], ea[2], -b2); j.k2 = fma(ea[0], ea[1], -a2);
+    /* adj_01 = b conj(c) - a e2 ; adj_02 = a c - b e1 ; adj_12 = conj(a) b - e0 c */
+    j.j01r = fma(A.br, A.cr, A.bi * A.ci) - A.ar * ea[2]; j.j01i = fma(A.bi, A.cr, -(A.br * A.ci)) - A.ai * ea[2];
+    j.j02r = fma(A.ar, A.cr, -(A.ai * A.ci)) - A.br * ea[1]; j.j02i = fma(A.ar, A.ci, A.ai * A.cr) - A.bi * ea[1];
+    j.j12r = fma(A.ar, A.br, A.ai * A.bi) - ea[0] * A.cr; j.j12i = fma(A.ar, A.bi, -(A.ai * A.br)) - ea[0] * A.ci;
+    return j;
 }
 
-/* tr(adj(A) B) for trace-free Hermitian A = (ea, A.offdiag), B = (eb, B.offdiag): the coefficient of
- * rho in det(A + rho B). */
-GF_HD double gfp_tr_adj(const double* ea, const gfp_herm3& A, const double* eb, const gfp_herm3& B) {
-    const double a2 = fma(A.ar, A.ar, A.ai * A.ai), b2 = fma(A.br, A.br, A.bi * A.bi), c2 = fma(A.cr, A.cr, A.ci * A.ci);
-    /* diagonal cofactors */
-    const double k0 = fma(ea[1], ea[2], -c2), k1 = fma(ea[0], ea[2], -b2), k2 = fma(ea[0], ea[1], -a2);
-    /* adj_01 = b conj(c) - a e2 ; adj_02 = a c - b e1 ; adj_12 = conj(a) b - e0 c */
-    const double j01r = fma(A.br, A.cr, A.bi * A.ci) - A.ar * ea[2], j01i = fma(A.bi, A.cr, -(A.br * A.ci)) - A.ai * ea[2];
-    const double j02r = fma(A.ar, A.cr, -(A.ai * A.ci)) - A.br * ea[1], j02i = fma(A.ar, A.ci, A.ai * A.cr) - A.bi * ea[1];
-    const double j12r = fma(A.ar, A.br, A.ai * A.bi) - ea[0] * A.cr, j12i = fma(A.ar, A.bi, -(A.ai * A.br)) - ea[0] * A.ci;
-    /* sum_ij adj_ij B_ji = sum_i k_i B_ii + 2 Re(adj_01 conj(B_01) + adj_02 conj(B_02) + adj_12 conj(B_12)) */
-    const double off = fma(j01r, B.ar, j01i * B.ai) + fma(j02r, B.br, j02i * B.bi) + fma(j12r, B.cr, j12i * B.ci);
-    return fma(2.0, off, fma(k0, eb[0], fma(k1, eb[1], k2 * eb[2])));
+/* tr(adj(A) B) = sum_i k_i B_ii + 2 Re(adj_01 conj(B_01) + adj_02 conj(B_02) + adj_12 conj(B_12)): the
+ * coefficient of rho in det(A + rho B) for trace-free Hermitian A, B = (eb, B.offdiag). */
+GF_HD double gfp_tr_adj_pre(const gfp_adj3& j, const double* eb, const gfp_herm3& B) {
+    const double off = fma(j.j01r, B.ar, j.j01i * B.ai) + fma(j.j02r, B.br, j.j02i * B.bi) + fma(j.j12r, B.cr, j.j12i * B.ci);
+    return fma(2.0, off, fma(j.k0, eb[0], fma(j.k1, eb[1], j.k2 * eb[2])));
 }
+
+GF_HD double gfp_tr_adj(const double* ea, const gfp_herm3& A, const double* eb, const gfp_herm3& B) {
+    return gfp_tr_adj_pre(gfp_adj_tf(ea, A), eb, B);
+}
+
+/* Q = tr(H'^2)/6 and det(H')/2 of a Hermitian matrix with eigenvalues (0, m1, m2): they depend on the
+ * spectrum alone, not on the mixing -- for H0 = U diag(0, m21, m3x) U^+ on the mass-squared differences
+ * only, for T = N diag(0, 1/100, 1) N^+ they are constants of the model whatever the NP angles. */
+GF_HD void gfp_spectrum_invariants(double m1, double m2, double& q, double& hdet) {
+    const double mu = (m1 + m2) * (1.0 / 3.0);
+    const double l0 = -mu, l1 = m1 - mu, l2 = m2 - mu;
+    q = (1.0 / 6.0) * fma(l0, l0, fma(l1, l1, l2 * l2));
+    hdet = 0.5 * (l0 * l1 * l2);
+}
+
+#define GFP_T_EIG1 0.01 /* sc1 = sc2 / 100, fr.py:381 */
+#define GFP_T_EIG2 1.0
 
 GF_HD gfp_pencil_T gfp_make_pencil_T(const gfp_herm3& T) {
     gfp_pencil_T t;
@@ -247,24 +266,23 @@ GF_HD gfp_pencil_T gfp_make_pencil_T(const gfp_herm3& T) {
     t.a22 = fma(T.ar, T.ar, T.ai * T.ai);
     t.b22 = fma(T.br, T.br, T.bi * T.bi);
     t.c22 = fma(T.cr, T.cr, T.ci * T.ci);
-    t.q2 = (1.0 / 6.0) * fma(2.0, t.a22 + t.b22 + t.c22, fma(t.te[0], t.te[0], fma(t.te[1], t.te[1], t.te[2] * t.te[2])));
-    t.d3 = 0.5 * gfp_det_tf(t.te, T);
+    gfp_spectrum_invariants(GFP_T_EIG1, GFP_T_EIG2, t.q2, t.d3);
     return t;
 }
 
-GF_HD gfp_pencil_P gfp_make_pencil_P(const gfp_herm3& h0, const gfp_herm3& T, const double* te) {
+/* h0 = U diag(0, m1, m2) U^+ (its spectrum-only invariants come from m1, m2), T with trace-free diagonal
+ * te; adjT = gfp_adj_tf(te, T) (a constant for the fixed textures). */
+GF_HD gfp_pencil_P gfp_make_pencil_P(const gfp_herm3& h0, double m1, double m2, const gfp_herm3& T, const double* te, const gfp_adj3& adjT) {
     gfp_pencil_P p;
     const double mu0 = (h0.d0 + h0.d1 + h0.d2) * (1.0 / 3.0);
     p.e[0] = h0.d0 - mu0; p.e[1] = h0.d1 - mu0; p.e[2] = h0.d2 - mu0;
     p.a2[0] = fma(h0.ar, h0.ar, h0.ai * h0.ai); p.a2[1] = 2.0 * fma(h0.ar, T.ar, h0.ai * T.ai);
     p.b2[0] = fma(h0.br, h0.br, h0.bi * h0.bi); p.b2[1] = 2.0 * fma(h0.br, T.br, h0.bi * T.bi);
     p.c2[0] = fma(h0.cr, h0.cr, h0.ci * h0.ci); p.c2[1] = 2.0 * fma(h0.cr, T.cr, h0.ci * T.ci);
-    const double sixth = 1.0 / 6.0;
-    p.q[0] = sixth * fma(2.0, p.a2[0] + p.b2[0] + p.c2[0], fma(p.e[0], p.e[0], fma(p.e[1], p.e[1], p.e[2] * p.e[2])));
-    p.q[1] = sixth * fma(2.0, p.a2[1] + p.b2[1] + p.c2[1], 2.0 * fma(p.e[0], te[0], fma(p.e[1], te[1], p.e[2] * te[2])));
-    p.d[0] = 0.5 * gfp_det_tf(p.e, h0);
+    gfp_spectrum_invariants(m1, m2, p.q[0], p.d[0]);
+    p.q[1] = (1.0 / 6.0) * fma(2.0, p.a2[1] + p.b2[1] + p.c2[1], 2.0 * fma(p.e[0], te[0], fma(p.e[1], te[1], p.e[2] * te[2])));
     p.d[1] = 0.5 * gfp_tr_adj(p.e, h0, te, T);
-    p.d[2] = 0.5 * gfp_tr_adj(te, T, p.e, h0);
+    p.d[2] = 0.5 * gfp_tr_adj_pre(adjT, p.e, h0);
     return p;
 }
 

@@ -20,11 +20,13 @@ extern std::atomic<unsigned long long> g_gf_launches;
 #ifndef GF_SCAN_THREADS
 #define GF_SCAN_THREADS 256
 #endif
-/* bins interleaved per thread in the scan kernels (see gf_bin_loop): 1 -- with the draw state on top
- * of the physics a second chain spills at 128 registers (A/B: 4.69e9 vs 4.78e9 samples/s) */
+/* bins interleaved per thread in the scan kernels (see gf_bin_loop): two independent chains wherever
+ * they fit into 128 registers without spilling -- the specialisations that keep the source (and the
+ * texture) in the constant bank; GF_SPEC_GENERIC (sampled source) spills with two and keeps one */
 #ifndef GF_SCAN_ILP
-#define GF_SCAN_ILP 1
+#define GF_SCAN_ILP 2
 #endif
+#define GF_SCAN_ILP_FOR(SPEC) ((SPEC) == GF_SPEC_GENERIC ? 1 : GF_SCAN_ILP)
 #ifndef GF_SCAN_MIN_BLOCKS
 #define GF_SCAN_MIN_BLOCKS 2
 #endif
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_S
             gf_draw_theta(m, seed, first_index + j, theta);
             gf_point q;
             gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
-            gf_point_fr<SPEC, GF_SCAN_ILP>(m, q, fr);
+            gf_point_fr<SPEC, GF_SCAN_ILP_FOR(SPEC)>(m, q, fr);
         } else {
             fr[0] = fr_in[3 * j];
             fr[1] = fr_in[3 * j + 1];
@@ -126,8 +128,14 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
     const int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
-    auto kern_s = spec == GF_SPEC_FIXED ? k_hist<SCAN, true, GF_SPEC_FIXED> : spec == GF_SPEC_SM ? k_hist<SCAN, true, GF_SPEC_SM> : k_hist<SCAN, true, GF_SPEC_GENERIC>;
-    auto kern_g = spec == GF_SPEC_FIXED ? k_hist<SCAN, false, GF_SPEC_FIXED> : spec == GF_SPEC_SM ? k_hist<SCAN, false, GF_SPEC_SM> : k_hist<SCAN, false, GF_SPEC_GENERIC>;
+    auto kern_s = spec == GF_SPEC_FIXED    ? k_hist<SCAN, true, GF_SPEC_FIXED>
+                  : spec == GF_SPEC_SM     ? k_hist<SCAN, true, GF_SPEC_SM>
+                  : spec == GF_SPEC_NPFREE ? k_hist<SCAN, true, GF_SPEC_NPFREE>
+                                           : k_hist<SCAN, true, GF_SPEC_GENERIC>;
+    auto kern_g = spec == GF_SPEC_FIXED    ? k_hist<SCAN, false, GF_SPEC_FIXED>
+                  : spec == GF_SPEC_SM     ? k_hist<SCAN, false, GF_SPEC_SM>
+                  : spec == GF_SPEC_NPFREE ? k_hist<SCAN, false, GF_SPEC_NPFREE>
+                                           : k_hist<SCAN, false, GF_SPEC_GENERIC>;
     int per_sm = 1;
     if (use_smem) {
         GF_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SCAN_MIN_BLOCKS)
         gf_draw_theta(m, seed, first_index + j, theta);
         gf_point q;
         gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
-        gf_point_fr<SPEC>(m, q, fr);
+        gf_point_fr<SPEC, GF_SCAN_ILP_FOR(SPEC)>(m, q, fr);
         const double ll = m.llh_kind == GF_LLH_FLAT
                               ? m.llh_const
                               : gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
