@@ -6,12 +6,19 @@
  * A step is two half-steps: every walker of half h proposes q = c_j - z (c_j - p) with a random
  * partner c_j from the OTHER half (which is not modified during that half-step), scores q with the
  * same per-point log-posterior as k_lnprob, and accepts or rejects in place.  Half-steps are
- * separated by a grid-wide barrier: one cooperative launch runs the whole chain when the batch is
- * co-resident (launch-latency free: the emcee shapes of 512..2048 points per half-step are far too
- * small to amortise a launch per half-step), otherwise the host issues one launch per half-step.
+ * separated by a barrier.  Launch shapes, all giving identical chains:
+ *   cluster : one thread-block CLUSTER per chain (up to 16 CTAs on 16 SMs of one GPC); the ensemble lives
+ *             in the distributed shared memory of the cluster for the whole run, partners are read with
+ *             ld.shared::cluster, half-steps are separated by the hardware cluster barrier.  The
+ *             latency-optimal shape for the emcee configurations (60 ... 8192 walkers).
+ *   block   : one block per chain with several walker pairs per thread (positions in global memory).
+ *   grid    : grid-wide barrier -- one cooperative launch when the batch is co-resident, otherwise one
+ *             launch per half-step.
+ * The per-point log-posterior is the same specialisation (gf_model_spec) that gf_lnprob launches.
  */
 #include <atomic>
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "gf_common.cuh"
 #include "gf_ensemble_dev.cuh"
@@ -20,9 +27,17 @@ namespace cg = cooperative_groups;
 extern std::atomic<unsigned long long> g_gf_launches;
 
 #define GF_ENS_THREADS 128
+/* energy bins interleaved per thread (gf_bin_loop): the sampler runs about one warp per SM sub-partition,
+ * so the latency of the eigen-stage chain is the step time -- interleave as many bins as registers allow */
+#ifndef GF_ENS_ILP_FIXED
+#define GF_ENS_ILP_FIXED 4
+#endif
+#ifndef GF_ENS_ILP_GENERIC
+#define GF_ENS_ILP_GENERIC 2
+#endif
 
 /* COOP: the whole run in one cooperative launch; otherwise one (step, half) per launch. */
-template <bool COOP>
+template <bool COOP, int SPEC, int ILP>
 __global__ void __launch_bounds__(GF_ENS_THREADS)
     k_ensemble(const __grid_constant__ gf_dev_model m, const gf_ens_args A, const int64_t one_step, const int one_half) {
     const int half = A.nwalkers / 2;
@@ -39,7 +54,7 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 if (active) {
-                    const unsigned acc = gf_ens_update(m, A, c, h * half + w, h, A.step0 + s);
+                    const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, h * half + w, h, A.step0 + s);
                     acc0 += h ? 0u : acc;
                     acc1 += h ? acc : 0u;
                 }
@@ -54,7 +69,7 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
     } else if (active) {
         const int64_t s = one_step;
         if (one_half < 2) {
-            const unsigned acc = gf_ens_update(m, A, c, one_half * half + w, one_half, A.step0 + s);
+            const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, one_half * half + w, one_half, A.step0 + s);
             acc0 = one_half ? 0u : acc;
             acc1 = one_half ? acc : 0u;
         }
@@ -77,6 +92,7 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
  * emcee configurations (60 ... 1024 walkers): no 2-3 us grid barrier twice per step.
  */
 #define GF_ENS_BLOCK_MAX 256
+template <int SPEC, int ILP>
 __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
     k_ensemble_block(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
     const int half = A.nwalkers / 2;
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             for (int w = threadIdx.x; w < half; w += blockDim.x) {
-                const unsigned acc = gf_ens_update(m, A, c, h * half + w, h, A.step0 + s);
+                const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, h * half + w, h, A.step0 + s);
                 if (acc && A.naccept) A.naccept[c * A.nwalkers + h * half + w] += 1ull; /* owned by this thread */
             }
             __threadfence_block();
@@ -95,6 +111,201 @@ __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
         if ((s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore)
             for (int k = threadIdx.x; k < A.nwalkers; k += blockDim.x) gf_ens_store(m, A, c, k, (s + 1) / A.thin - 1, nstore);
     }
+}
+
+
+/*
+ * Cluster-per-chain variant.  CTA `rank` of the cluster owns walkers [rank*T, (rank+1)*T) of BOTH halves
+ * (thread = walker pair, as above); positions and log-posteriors stay in its shared memory
+ * (sh = pos[2][T][ndim], lnp[2][T]) from the first step to the last.  During half-step h every thread
+ * reads its partner from the OTHER half through distributed shared memory -- that half is not written
+ * during the half-step -- and updates its own walker of half h in place; the cluster barrier
+ * (barrier.cluster arrive.release / wait.acquire) orders the two.  No global-memory round trip and no
+ * grid barrier on the critical path: a half-step costs one log-posterior latency plus the barrier.
+ */
+/* threads per CTA: 256 for the register-light SM-only models, 128 for the BSM path (full register file
+ * for the eigen stage: no spills on the latency-critical path) */
+#define GF_ENS_CL_MAX_THREADS(SPEC) ((SPEC) == GF_SPEC_SM ? 256 : 128)
+template <int SPEC, int ILP>
+__global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
+    k_ensemble_cluster(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
+    extern __shared__ double sh_ens[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int T = (int)blockDim.x, ndim = m.ndim, half = A.nwalkers / 2;
+    const int nc = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int64_t c = blockIdx.x / nc;
+    const int wl = (int)threadIdx.x, w = rank * T + wl;
+    const bool active = w < half;
+    double* pos_s = sh_ens;
+    double* lnp_s = sh_ens + 2 * T * ndim;
+    const int64_t nstore = A.nsteps / A.thin;
+    if (active) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int64_t k = c * A.nwalkers + h * half + w;
+            for (int d = 0; d < ndim; ++d) pos_s[(h * T + wl) * ndim + d] = A.pos[k * ndim + d];
+            lnp_s[h * T + wl] = A.lnp[k];
+        }
+    }
+    cluster.sync();
+    unsigned acc0 = 0u, acc1 = 0u;
+    const uint64_t gid0 = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)w;
+    for (int64_t s = 0; s < A.nsteps; ++s) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            if (active) {
+                const gf_ens_draw dr = gf_ens_draws(A, gid0 + (uint64_t)(h * half), A.step0 + s, half);
+                const int rj = dr.j / T, jl = dr.j - rj * T;
+                const double* cj = cluster.map_shared_rank(pos_s + ((1 - h) * T + jl) * ndim, rj);
+                double* p = pos_s + (h * T + wl) * ndim;
+                double q[GF_MAX_DIM];
+                for (int d = 0; d < ndim; ++d) q[d] = gf_ens_stretch(cj[d], p[d], dr.z);
+                double lnew;
+                if (gf_ens_accept<SPEC, ILP>(m, A, dr, q, lnp_s[h * T + wl], lnew)) {
+                    for (int d = 0; d < ndim; ++d) p[d] = q[d];
+                    lnp_s[h * T + wl] = lnew;
+                    acc0 += h ? 0u : 1u;
+                    acc1 += h ? 1u : 0u;
+                }
+            }
+            cluster.sync();
+        }
+        if (active && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) {
+            const int64_t slot = (s + 1) / A.thin - 1;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int64_t k = c * A.nwalkers + h * half + w;
+                if (A.chain)
+                    for (int d = 0; d < ndim; ++d) A.chain[(k * nstore + slot) * ndim + d] = pos_s[(h * T + wl) * ndim + d];
+                if (A.lnp_chain) A.lnp_chain[k * nstore + slot] = lnp_s[h * T + wl];
+            }
+        }
+    }
+    if (active) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int64_t k = c * A.nwalkers + h * half + w;
+            for (int d = 0; d < ndim; ++d) A.pos[k * ndim + d] = pos_s[(h * T + wl) * ndim + d];
+            A.lnp[k] = lnp_s[h * T + wl];
+        }
+        if (A.naccept) { /* owned by this thread */
+            A.naccept[c * A.nwalkers + w] += (unsigned long long)acc0;
+            A.naccept[c * A.nwalkers + half + w] += (unsigned long long)acc1;
+        }
+    }
+    /* the last cluster.sync() of the step loop (or the one after the load) already guarantees that no
+     * CTA reads a peer's shared memory after this point */
+}
+
+/* cluster geometry for (nchains, half): the smallest power-of-two cluster that leaves at most one warp
+ * per SM sub-partition (T <= 128), as long as the clusters of all chains fit the SMs at once; never
+ * more than 16 CTAs (the non-portable maximum) or max_threads per CTA.  Returns false if the ensemble
+ * does not fit a cluster. */
+static bool cluster_geometry(int64_t nchains, int half, int sms, int want_nc, int max_threads, int* nc_out, int* threads_out) {
+    int nc = 1;
+    if (want_nc > 0) {
+        while (nc < want_nc && nc < 16) nc *= 2;
+    } else {
+        while (nc < 16 && (half + nc - 1) / nc > 128 && nchains * (nc * 2) <= (int64_t)sms) nc *= 2;
+    }
+    while (nc < 16 && (half + nc - 1) / nc > max_threads) nc *= 2;
+    int threads = (((half + nc - 1) / nc) + 31) / 32 * 32;
+    if (threads > max_threads) return false;
+    while (nc > 1 && (nc / 2) * threads >= half) nc /= 2; /* rounding to warps may have emptied the last CTAs */
+    *nc_out = nc;
+    *threads_out = threads;
+    return true;
+}
+
+template <int SPEC, int ILP>
+static int launch_cluster(const gf_dev_model& d, const gf_ens_args& A, int nc, int threads, cudaStream_t st, bool* launched) {
+    auto kern = k_ensemble_cluster<SPEC, ILP>;
+    const size_t smem = (size_t)(2 * threads * d.ndim + 2 * threads) * sizeof(double);
+    GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (nc > 8) GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(A.nchains * nc));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nc;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError(); /* this cluster size cannot be scheduled here: the caller falls back */
+        *launched = false;
+        return GF_OK;
+    }
+    GF_CUDA(cudaLaunchKernelEx(&cfg, kern, d, A));
+    ++g_gf_launches;
+    *launched = true;
+    return GF_OK;
+}
+
+template <int SPEC, int ILP>
+static int run_spec(const gf_dev_model& d, const gf_ens_args& A, const gf_ensemble_config* cfg, cudaStream_t st) {
+    const int half = cfg->nwalkers / 2;
+    const int64_t total = cfg->nchains * half;
+    const unsigned blocks = gf_blocks_for(total, GF_ENS_THREADS);
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    /* auto: the cluster shape whenever the ensemble fits one (<= 16 x 256 walker pairs, 16 x 128 on the BSM path) */
+    if (cfg->mode == 3 || cfg->mode == 0) {
+        int nc = 0, threads = 0;
+        if (cluster_geometry(cfg->nchains, half, sms, cfg->cluster_blocks, GF_ENS_CL_MAX_THREADS(SPEC), &nc, &threads)) {
+            for (;;) {
+                bool launched = false;
+                if (int rc = launch_cluster<SPEC, ILP>(d, A, nc, threads, st, &launched)) return rc;
+                if (launched) {
+                    GF_LAUNCH_CHECK("k_ensemble_cluster");
+                    return GF_OK;
+                }
+                /* this cluster size cannot be scheduled on the device: halve it while the CTA still holds its share */
+                nc /= 2;
+                threads = nc >= 1 ? (((half + nc - 1) / nc) + 31) / 32 * 32 : 0;
+                if (nc < 1 || threads > GF_ENS_CL_MAX_THREADS(SPEC)) break;
+            }
+        }
+        GF_REQUIRE(cfg->mode == 0, "gf_ensemble_run: mode 3 (cluster per chain) cannot hold %d walkers per chain", cfg->nwalkers);
+    }
+    /* block mode only when every thread owns ONE walker pair -- a second sequential pass per half-step
+     * costs more than the grid barrier it saves (measured: 1024 walkers, 24 vs 12 us / step) */
+    if (cfg->mode == 2 || (cfg->mode == 0 && half <= GF_ENS_BLOCK_MAX)) {
+        const int threads = half >= GF_ENS_BLOCK_MAX ? GF_ENS_BLOCK_MAX : ((half + 31) / 32) * 32;
+        k_ensemble_block<SPEC, ILP><<<(unsigned)cfg->nchains, threads, 0, st>>>(d, A);
+        ++g_gf_launches;
+        GF_LAUNCH_CHECK("k_ensemble_block");
+        return GF_OK;
+    }
+    int dev = 0, coop = 0, per_sm = 0;
+    GF_CUDA(cudaGetDevice(&dev));
+    GF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ensemble<true, SPEC, ILP>, GF_ENS_THREADS, 0));
+    if (coop && (int64_t)blocks <= (int64_t)sms * per_sm) {
+        int64_t one_step = 0;
+        int one_half = 0;
+        void* params[] = {(void*)&d, (void*)&A, (void*)&one_step, (void*)&one_half};
+        GF_CUDA(cudaLaunchCooperativeKernel((const void*)k_ensemble<true, SPEC, ILP>, dim3(blocks), dim3(GF_ENS_THREADS), params, 0, st));
+        ++g_gf_launches;
+        return GF_OK;
+    }
+    for (int64_t s = 0; s < cfg->nsteps; ++s) {
+        for (int h = 0; h < 2; ++h) {
+            k_ensemble<false, SPEC, ILP><<<blocks, GF_ENS_THREADS, 0, st>>>(d, A, s, h);
+            ++g_gf_launches;
+        }
+        if ((A.chain || A.lnp_chain) && (s + 1) % cfg->thin == 0) {
+            k_ensemble<false, SPEC, ILP><<<blocks, GF_ENS_THREADS, 0, st>>>(d, A, s, 2);
+            ++g_gf_launches;
+        }
+        GF_LAUNCH_CHECK("k_ensemble");
+    }
+    return GF_OK;
 }
 
 extern "C" int gf_ensemble_run(const gf_model* model, const gf_ensemble_config* cfg, double* d_pos, double* d_lnp, double* d_chain,
@@ -115,44 +326,12 @@ extern "C" int gf_ensemble_run(const gf_model* model, const gf_ensemble_config* 
     A.nchains = cfg->nchains; A.nsteps = cfg->nsteps; A.step0 = cfg->step0; A.thin = cfg->thin;
     A.nwalkers = cfg->nwalkers; A.nfree = cfg->nfree; A.a = cfg->a; A.seed = cfg->seed; A.chain0 = cfg->chain0;
     A.pos = d_pos; A.lnp = d_lnp; A.chain = d_chain; A.lnp_chain = d_lnp_chain; A.naccept = d_naccept;
-    const int64_t total = cfg->nchains * (cfg->nwalkers / 2);
-    const unsigned blocks = gf_blocks_for(total, GF_ENS_THREADS);
     cudaStream_t st = (cudaStream_t)stream;
-
-    const int half = cfg->nwalkers / 2;
-    GF_REQUIRE(cfg->mode >= 0 && cfg->mode <= 2, "gf_ensemble_run: mode = %d outside [0, 2]", cfg->mode);
-    /* auto: block mode only when every thread owns ONE walker pair -- a second sequential pass per
-     * half-step costs more than the grid barrier it saves (measured: 1024 walkers, 24 vs 12 us / step) */
-    if (cfg->mode == 2 || (cfg->mode == 0 && half <= GF_ENS_BLOCK_MAX)) {
-        const int threads = half >= GF_ENS_BLOCK_MAX ? GF_ENS_BLOCK_MAX : ((half + 31) / 32) * 32;
-        k_ensemble_block<<<(unsigned)cfg->nchains, threads, 0, st>>>(d, A);
-        ++g_gf_launches;
-        GF_LAUNCH_CHECK("k_ensemble_block");
-        return GF_OK;
-    }
-    int dev = 0, coop = 0, sms = 0, per_sm = 0;
-    GF_CUDA(cudaGetDevice(&dev));
-    GF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    if (int rc = gf_sm_count(&sms)) return rc;
-    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ensemble<true>, GF_ENS_THREADS, 0));
-    if (coop && (int64_t)blocks <= (int64_t)sms * per_sm) {
-        int64_t one_step = 0;
-        int one_half = 0;
-        void* params[] = {(void*)&d, (void*)&A, (void*)&one_step, (void*)&one_half};
-        GF_CUDA(cudaLaunchCooperativeKernel((const void*)k_ensemble<true>, dim3(blocks), dim3(GF_ENS_THREADS), params, 0, st));
-        ++g_gf_launches;
-        return GF_OK;
-    }
-    for (int64_t s = 0; s < cfg->nsteps; ++s) {
-        for (int h = 0; h < 2; ++h) {
-            k_ensemble<false><<<blocks, GF_ENS_THREADS, 0, st>>>(d, A, s, h);
-            ++g_gf_launches;
-        }
-        if ((d_chain || d_lnp_chain) && (s + 1) % cfg->thin == 0) {
-            k_ensemble<false><<<blocks, GF_ENS_THREADS, 0, st>>>(d, A, s, 2);
-            ++g_gf_launches;
-        }
-        GF_LAUNCH_CHECK("k_ensemble");
-    }
-    return GF_OK;
+    GF_REQUIRE(cfg->mode >= 0 && cfg->mode <= 3, "gf_ensemble_run: mode = %d outside [0, 3]", cfg->mode);
+    GF_REQUIRE(cfg->cluster_blocks >= 0 && cfg->cluster_blocks <= 16, "gf_ensemble_run: cluster_blocks = %d outside [0, 16]", cfg->cluster_blocks);
+    /* the per-point log-posterior specialisation gf_lnprob launches for this model (NPFREE -> GENERIC) */
+    const int spec = gf_model_spec(d);
+    if (spec == GF_SPEC_SM) return run_spec<GF_SPEC_SM, 1>(d, A, cfg, st);
+    if (spec == GF_SPEC_FIXED) return run_spec<GF_SPEC_FIXED, GF_ENS_ILP_FIXED>(d, A, cfg, st);
+    return run_spec<GF_SPEC_GENERIC, GF_ENS_ILP_GENERIC>(d, A, cfg, st);
 }

@@ -34,32 +34,53 @@ struct gf_ens_args {
     unsigned long long* naccept;
 };
 
-/* one stretch-move update of walker k (in half h) of chain c */
+/* The three Philox words of one update (see gf_ensemble_config): stretch factor z, partner index j in
+ * the other half, and the uniform of the acceptance test. */
+struct gf_ens_draw {
+    double z, u_accept;
+    int j;
+};
+
+GF_HD gf_ens_draw gf_ens_draws(const gf_ens_args& A, uint64_t gid, int64_t step, int half) {
+    const uint64_t s = (uint64_t)step;
+    const gf_u4 r = gf_philox4x32_10((uint32_t)gid, (uint32_t)s, (uint32_t)(s >> 32), 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+    gf_ens_draw d;
+    /* no FMA contraction in the proposal: bit-reproducible with NumPy */
+    const double t = GF_ADD_RN(GF_MUL_RN(A.a - 1.0, gf_u01(r.x)), 1.0);
+    d.z = GF_DIV_RN(GF_MUL_RN(t, t), A.a);
+    int j = (int)(gf_u01(r.y) * (double)half);
+    d.j = j < half ? j : half - 1;
+    d.u_accept = gf_u01(r.z);
+    return d;
+}
+
+/* q = c_j - z (c_j - p), contraction-free */
+GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(cd, GF_MUL_RN(z, GF_SUB_RN(cd, pd))); }
+
+/* score the proposal q and decide: accept iff (nfree-1) ln z + lnp(q) - lnp(p) > ln u (false for NaN) */
+template <int SPEC, int ILP>
+GF_HD bool gf_ens_accept(const gf_dev_model& m, const gf_ens_args& A, const gf_ens_draw& dr, const double* q, double lold, double& lnew) {
+    double fr[3];
+    unsigned st = 0u;
+    lnew = gf_point_lnprob<SPEC, ILP>(m, [&](int d) { return q[d]; }, fr, st);
+    const double diff = (double)(A.nfree - 1) * log(dr.z) + lnew - lold;
+    return diff > log(dr.u_accept);
+}
+
+/* one stretch-move update of walker k (in half h) of chain c, positions in global memory */
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int h, int64_t step) {
     const int ndim = m.ndim, half = A.nwalkers / 2;
     const uint64_t gid = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)k;
-    const uint64_t s = (uint64_t)step;
-    const gf_u4 r = gf_philox4x32_10((uint32_t)gid, (uint32_t)s, (uint32_t)(s >> 32), 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
-    /* no FMA contraction in the proposal: bit-reproducible with NumPy */
-    const double t = GF_ADD_RN(GF_MUL_RN(A.a - 1.0, gf_u01(r.x)), 1.0);
-    const double z = GF_DIV_RN(GF_MUL_RN(t, t), A.a);
-    int j = (int)(gf_u01(r.y) * (double)half);
-    j = j < half ? j : half - 1;
+    const gf_ens_draw dr = gf_ens_draws(A, gid, step, half);
     const double* p = A.pos + (c * A.nwalkers + k) * ndim;
-    const double* cj = A.pos + (c * A.nwalkers + (1 - h) * half + j) * ndim;
+    const double* cj = A.pos + (c * A.nwalkers + (1 - h) * half + dr.j) * ndim;
     double q[GF_MAX_DIM];
     /* positions of other walkers were written by other SMs before the last grid barrier: read them
      * through L2 (ld.global.cg), not through this SM's non-coherent L1 */
-    for (int d = 0; d < ndim; ++d) {
-        const double cd = GF_LDCG(cj + d);
-        q[d] = GF_SUB_RN(cd, GF_MUL_RN(z, GF_SUB_RN(cd, GF_LDCG(p + d))));
-    }
-    double fr[3];
-    unsigned st = 0u;
-    const double lnew = gf_point_lnprob(m, [&](int d) { return q[d]; }, fr, st);
-    const double lold = GF_LDCG(A.lnp + c * A.nwalkers + k);
-    const double diff = (double)(A.nfree - 1) * log(z) + lnew - lold;
-    const bool accept = diff > log(gf_u01(r.z)); /* false for NaN */
+    for (int d = 0; d < ndim; ++d) q[d] = gf_ens_stretch(GF_LDCG(cj + d), GF_LDCG(p + d), dr.z);
+    double lnew;
+    const bool accept = gf_ens_accept<SPEC, ILP>(m, A, dr, q, GF_LDCG(A.lnp + c * A.nwalkers + k), lnew);
     if (accept) {
         double* pw = A.pos + (c * A.nwalkers + k) * ndim;
         for (int d = 0; d < ndim; ++d) pw[d] = q[d];

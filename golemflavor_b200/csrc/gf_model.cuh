@@ -117,40 +117,44 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
                            double lam, double s2, double sd0, double sd1, double inv_norm, double S, double* fr) {
     unsigned st = 0u;
     double a0 = 0.0, a1 = 0.0;
-    /* ILP = 2: two bins per iteration, i.e. two independent fast-path chains in flight per thread
-     * (+10 % on k_lnprob, which is bound by the latency of that chain at 16 warps per SM); kernels with
-     * more per-thread state (the scans) keep ILP = 1 because the second chain would spill */
+    /* ILP bins per iteration, i.e. ILP independent fast-path chains in flight per thread.  2: +10 % on
+     * k_lnprob, which is bound by the latency of that chain at 16 warps per SM; 1: kernels whose extra
+     * per-thread state would make the second chain spill; 4: the ensemble sampler, where a single warp
+     * per SM sub-partition runs the chain and latency is all that matters */
     int b = 0;
-    for (; ILP == 2 && b + 1 < m.nbins; b += 2) {
-        const double rho0 = lam * m.g[b], rho1 = lam * m.g[b + 1];
-        gfp_x4 x0, x1;
-        const bool ok0 = gfp_pencil_x4_fast(pp, pt, rho0, x0);
-        const bool ok1 = gfp_pencil_x4_fast(pp, pt, rho1, x1);
-        if (!(ok0 && ok1)) { /* rare: Jacobi for whichever bin failed; separate objects keep x0/x1 in registers */
-            if (!ok0) {
-                gfp_x4 slow;
-                st |= gfp_pencil_x4_jacobi(&h0, &T, rho0, &slow);
-                x0 = slow;
+    if (ILP > 1) {
+        for (; b + ILP <= m.nbins; b += ILP) {
+            gfp_x4 x[ILP];
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) ok = gfp_pencil_x4_fast(pp, pt, lam * m.g[b + i], x[i]) && ok;
+            if (!ok) { /* rare: Jacobi for whichever bin failed (re-tested: the flags are not kept in registers) */
+#pragma unroll
+                for (int i = 0; i < ILP; ++i) {
+                    gfp_x4 again;
+                    if (!gfp_pencil_x4_fast(pp, pt, lam * m.g[b + i], again)) {
+                        gfp_x4 slow; /* a separate object keeps x[] in registers */
+                        st |= gfp_pencil_x4_refine(&h0, &T, lam * m.g[b + i], &slow);
+                        x[i] = slow;
+                    }
+                }
             }
-            if (!ok1) {
-                gfp_x4 slow;
-                st |= gfp_pencil_x4_jacobi(&h0, &T, rho1, &slow);
-                x1 = slow;
+#pragma unroll
+            for (int i = 0; i < ILP; ++i) {
+                double f0, f1;
+                gfp_mix4(x[i], s2, sd0, sd1, S, f0, f1);
+                const double wd = m.width[b + i];
+                a0 = fma(wd, f0, a0);
+                a1 = fma(wd, f1, a1);
             }
         }
-        double f00, f01, f10, f11;
-        gfp_mix4(x0, s2, sd0, sd1, S, f00, f01);
-        gfp_mix4(x1, s2, sd0, sd1, S, f10, f11);
-        const double wd0 = m.width[b], wd1 = m.width[b + 1];
-        a0 = fma(wd1, f10, fma(wd0, f00, a0));
-        a1 = fma(wd1, f11, fma(wd0, f01, a1));
     }
-    for (; b < m.nbins; ++b) { /* ILP = 1, or the last of an odd number of bins */
+    for (; b < m.nbins; ++b) { /* ILP = 1, or the remaining bins */
         const double rho = lam * m.g[b];
         gfp_x4 x;
         if (!gfp_pencil_x4_fast(pp, pt, rho, x)) {
             gfp_x4 slow;
-            st |= gfp_pencil_x4_jacobi(&h0, &T, rho, &slow);
+            st |= gfp_pencil_x4_refine(&h0, &T, rho, &slow);
             x = slow;
         }
         double f0, f1;

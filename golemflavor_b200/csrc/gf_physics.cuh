@@ -49,7 +49,9 @@
 
 /* Relative eigenvalue gap (in units of 2 sqrt(Q)) below which the closed-form path hands over
  * to Jacobi: the closed form loses accuracy like eps/gap^2, Jacobi like eps/gap. */
+#ifndef GFP_FAST_MIN_SIN2
 #define GFP_FAST_MIN_SIN2 1.4e-6 /* sin^2(phi/3): gap = sqrt(3 * sin^2) ~ 2.0e-3 */
+#endif
 #define GFP_ILL_GAP 1e-6
 
 /* ------------------------------------------------------------------ fast fp64 helpers */
@@ -367,10 +369,72 @@ GF_HD_NOINLINE double gfp_herm3_jacobi(const gfp_herm3& h, double* lam, double* 
     return spread > 0.0 ? gmin / spread : 0.0;
 }
 
-/* Fallback of the energy-bin loop: rebuild H = H0 + rho T, run Jacobi, return the same four
- * entries as the fast path.  Out of line, operands by pointer: only the rare slow path pays for
- * the memory round trip.  Returns status bits (REFINED / ILL_COND / NON_FINITE). */
-GF_HD_NOINLINE unsigned gfp_pencil_x4_jacobi(const gfp_herm3* h0, const gfp_herm3* T, double rho, gfp_x4* out) {
+/*
+ * Refinement of a near-degenerate eigenvalue pair by DEFLATION (single matrix).
+ *
+ * The closed form loses accuracy like eps/gap^2 when two eigenvalues approach each other -- through the
+ * characteristic polynomial, whose close roots are ill-conditioned in its coefficients.  The ISOLATED
+ * eigenvalue l0 and its eigenvector stay well-conditioned, so the matrix itself is used for the pair:
+ *   A = H' - l0, adj(A) = p'(l0) v0 v0^+  (exact for the exact l0)  =>  W = v0 v0^+ = adj(A) / tr adj(A);
+ *   with m = -l0/2 the pair's midpoint, F = (H' - m) - (3/2) l0 W = h (v1 v1^+ - v2 v2^+),
+ *   h^2 = tr(F^2)/2 (half the pair's splitting), and on the diagonal F_aa = h (|V_a1|^2 - |V_a2|^2).
+ * Every entry of F is a difference of O(|H|) terms formed once, so |V_a1|^2, |V_a2|^2 come out with error
+ * eps |H| / h -- the conditioning of the eigenvectors themselves, which is also what Jacobi delivers, at
+ * ~150 instead of several thousand fp64 operations and without loops or local-memory arrays.
+ * Returns status bits; GFP_ST_NON_FINITE asks the caller for the Jacobi solver (degenerate scale, NaN).
+ */
+GF_HD unsigned gfp_herm3_x4_deflate(const gfp_herm3& h, gfp_x4& out) {
+    const double mu = (h.d0 + h.d1 + h.d2) * (1.0 / 3.0);
+    const double e0 = h.d0 - mu, e1 = h.d1 - mu, e2 = h.d2 - mu;
+    const double a2 = fma(h.ar, h.ar, h.ai * h.ai), b2 = fma(h.br, h.br, h.bi * h.bi), c2 = fma(h.cr, h.cr, h.ci * h.ci);
+    const double Q = (1.0 / 6.0) * fma(2.0, a2 + b2 + c2, fma(e0, e0, fma(e1, e1, e2 * e2)));
+    if (!(Q > 1e-280 && Q < 1e280)) return GFP_ST_NON_FINITE;
+    const double acr = fma(h.ar, h.cr, -(h.ai * h.ci)), aci = fma(h.ar, h.ci, h.ai * h.cr);
+    const double tri = fma(acr, h.br, aci * h.bi);
+    const double hdet = 0.5 * (fma(2.0, tri, e0 * e1 * e2) - fma(e0, c2, fma(e1, b2, e2 * a2)));
+    const double rs = gfp_rsqrt(Q);
+    const double r = (hdet * rs) * (rs * rs);
+    const double delta = fmax(1.0 - fabs(r), 0.0);
+    const double w = gfp_cubic_w(delta);
+    const double sq = 2.0 * Q * rs;
+    const double l0 = copysign(sq - sq * w, r); /* isolated eigenvalue, absolute error ~ eps sqrt(Q) */
+    /* adj(H' - l0): real diagonal cofactors and the upper triangle */
+    const double g0 = e0 - l0, g1 = e1 - l0, g2 = e2 - l0;
+    const double k0 = fma(g1, g2, -c2), k1 = fma(g0, g2, -b2), k2 = fma(g0, g1, -a2);
+    const double j01r = fma(h.br, h.cr, h.bi * h.ci) - h.ar * g2, j01i = fma(h.bi, h.cr, -(h.br * h.ci)) - h.ai * g2;
+    const double j02r = acr - h.br * g1, j02i = aci - h.bi * g1;
+    const double j12r = fma(h.ar, h.br, h.ai * h.bi) - g0 * h.cr, j12i = fma(h.ar, h.bi, -(h.ai * h.br)) - g0 * h.ci;
+    const double ip = gfp_rcp(k0 + k1 + k2); /* tr adj = p'(l0) = (l0 - l1)(l0 - l2) in [6 Q, 9 Q] */
+    const double t = 1.5 * l0 * ip;
+    const double m = -0.5 * l0;
+    /* F = (H' - m) - (3/2) l0 W */
+    const double n0 = fma(-t, k0, e0 - m), n1 = fma(-t, k1, e1 - m), n2 = fma(-t, k2, e2 - m);
+    const double f01r = fma(-t, j01r, h.ar), f01i = fma(-t, j01i, h.ai);
+    const double f02r = fma(-t, j02r, h.br), f02i = fma(-t, j02i, h.bi);
+    const double f12r = fma(-t, j12r, h.cr), f12i = fma(-t, j12i, h.ci);
+    const double h2 = fma(0.5, fma(n0, n0, fma(n1, n1, n2 * n2)),
+                          fma(f01r, f01r, f01i * f01i) + fma(f02r, f02r, f02i * f02i) + fma(f12r, f12r, f12i * f12i));
+    const double hh = sqrt(h2);
+    const double ih = hh > 0.0 ? 1.0 / hh : 0.0; /* exactly degenerate pair: split it evenly */
+    const double x00 = k0 * ip, x10 = k1 * ip;
+    out.x00 = x00;
+    out.x10 = x10;
+    /* |V_a1|^2 - |V_a2|^2 = n_a / h lies in [-(1 - x_a0), 1 - x_a0]; round-off of a (nearly) degenerate
+     * pair must not leave that range */
+    out.x01 = fmin(fmax(0.5 * fma(n0, ih, 1.0 - x00), 0.0), fmax(1.0 - x00, 0.0));
+    out.x11 = fmin(fmax(0.5 * fma(n1, ih, 1.0 - x10), 0.0), fmax(1.0 - x10, 0.0));
+    unsigned st = GFP_ST_REFINED;
+    const double relgap = 2.0 * hh / (1.5 * fabs(l0) + hh);
+    if (!(relgap >= GFP_ILL_GAP)) st |= GFP_ST_ILL_COND;
+    if (!(fabs(out.x00) + fabs(out.x01) + fabs(out.x10) + fabs(out.x11) < 1e300)) st |= GFP_ST_NON_FINITE;
+    return st;
+}
+
+/* Fallback of the energy-bin loop: rebuild H = H0 + rho T and refine by deflation (Jacobi only for a
+ * degenerate scale or non-finite input), return the same four entries as the fast path.  Out of line,
+ * operands by pointer: only the rare slow path pays for the memory round trip.  Returns status bits
+ * (REFINED / ILL_COND / NON_FINITE). */
+GF_HD_NOINLINE unsigned gfp_pencil_x4_refine(const gfp_herm3* h0, const gfp_herm3* T, double rho, gfp_x4* out) {
     gfp_herm3 h;
     h.d0 = fma(rho, T->d0, h0->d0);
     h.d1 = fma(rho, T->d1, h0->d1);
@@ -381,15 +445,20 @@ GF_HD_NOINLINE unsigned gfp_pencil_x4_jacobi(const gfp_herm3* h0, const gfp_herm
     h.bi = fma(rho, T->bi, h0->bi);
     h.cr = fma(rho, T->cr, h0->cr);
     h.ci = fma(rho, T->ci, h0->ci);
-    double lam[3], vr[9], vi[9];
-    const double relgap = gfp_herm3_jacobi(h, lam, vr, vi);
-    unsigned st = GFP_ST_REFINED;
-    out->x00 = fma(vr[0], vr[0], vi[0] * vi[0]);
-    out->x01 = fma(vr[1], vr[1], vi[1] * vi[1]);
-    out->x10 = fma(vr[3], vr[3], vi[3] * vi[3]);
-    out->x11 = fma(vr[4], vr[4], vi[4] * vi[4]);
-    if (!(relgap >= GFP_ILL_GAP)) st |= GFP_ST_ILL_COND;
-    if (!(fabs(out->x00) + fabs(out->x01) + fabs(out->x10) + fabs(out->x11) < 1e300)) st |= GFP_ST_NON_FINITE;
+    gfp_x4 x;
+    unsigned st = gfp_herm3_x4_deflate(h, x);
+    if (st & GFP_ST_NON_FINITE) {
+        double lam[3], vr[9], vi[9];
+        const double relgap = gfp_herm3_jacobi(h, lam, vr, vi);
+        st = GFP_ST_REFINED;
+        x.x00 = fma(vr[0], vr[0], vi[0] * vi[0]);
+        x.x01 = fma(vr[1], vr[1], vi[1] * vi[1]);
+        x.x10 = fma(vr[3], vr[3], vi[3] * vi[3]);
+        x.x11 = fma(vr[4], vr[4], vi[4] * vi[4]);
+        if (!(relgap >= GFP_ILL_GAP)) st |= GFP_ST_ILL_COND;
+        if (!(fabs(x.x00) + fabs(x.x01) + fabs(x.x10) + fabs(x.x11) < 1e300)) st |= GFP_ST_NON_FINITE;
+    }
+    *out = x;
     return st;
 }
 

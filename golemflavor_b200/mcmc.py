@@ -174,7 +174,7 @@ class DeviceEnsembleSampler(object):
     identical in all walkers of a chain stay frozen; pass ``nfree`` = number of sampled dimensions.
     """
 
-    def __init__(self, nwalkers, ndim, lnprob, nchains=1, a=2.0, seed=0, nfree=None, store_lnprob=True, chain0=0, mode=0):
+    def __init__(self, nwalkers, ndim, lnprob, nchains=1, a=2.0, seed=0, nfree=None, store_lnprob=True, chain0=0, mode=0, cluster_blocks=0):
         from . import _lib
         if nwalkers % 2 != 0:
             raise ValueError('The number of walkers must be even.')
@@ -186,7 +186,8 @@ class DeviceEnsembleSampler(object):
         if self.k < 2 * self.nfree:
             raise ValueError('The number of walkers needs to be more than twice the dimension of your parameter space.')
         self.lnprob, self.seed, self.store_lnprob, self.chain0 = lnprob, int(seed), bool(store_lnprob), int(chain0)
-        self.mode = int(mode)   # 0 auto, 1 grid barrier, 2 block per chain (gf_ensemble_config.mode)
+        self.mode = int(mode)   # 0 auto, 1 grid barrier, 2 block per chain, 3 cluster per chain (gf_ensemble_config.mode)
+        self.cluster_blocks = int(cluster_blocks)   # CTAs per cluster, 0 = auto
         self.total_steps = 0   # global step counter = RNG counter offset: continuing a run never reuses draws
         self._last = None
         self.reset()
@@ -253,7 +254,7 @@ class DeviceEnsembleSampler(object):
         if self._naccept is None:
             self._naccept = torch.zeros((self.nchains, self.k), dtype=torch.int64, device='cuda')
         cfg = _lib.EnsembleConfig(nchains=self.nchains, nwalkers=self.k, nfree=self.nfree, nsteps=int(N),
-                                  step0=self.total_steps, thin=int(thin), a=self.a, seed=self.seed, chain0=self.chain0, mode=self.mode)
+                                  step0=self.total_steps, thin=int(thin), a=self.a, seed=self.seed, chain0=self.chain0, mode=self.mode, cluster_blocks=self.cluster_blocks)
         _lib.check(_lib.load().gf_ensemble_run(self.lnprob.model.ref, C.byref(cfg), _lib.ptr(pos), _lib.ptr(lnp),
                                                _lib.ptr(chain), _lib.ptr(lchain), _lib.ptr(self._naccept),
                                                _lib.stream_ptr(torch)))

@@ -216,9 +216,10 @@ int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells, double cov
  * Device-resident affine-invariant ensemble sampler: the stretch move of emcee's EnsembleSampler
  * (Goodman & Weare 2010; red/blue half-ensembles, parameter a) that golemflavor/mcmc.py:27-53 drives
  * from Python, for `nchains` INDEPENDENT ensembles of `nwalkers` walkers at once (one thread per
- * walker pair; ensembles whose half fits one thread block -- up to 512 walkers -- live in one block per
- * chain with block-level barriers; larger ones run as one cooperative launch with a grid barrier per
- * half-step when the batch is co-resident, one launch per half-step otherwise; all three shapes give
+ * walker pair; ensembles of up to 4096 walkers (8192 for SM-only models) live in the distributed shared memory of one thread-block
+ * cluster per chain and synchronise with the hardware cluster barrier; the other shapes -- one block per
+ * chain with global-memory positions, one cooperative launch with a grid barrier per half-step when the
+ * batch is co-resident, one launch per half-step otherwise -- remain selectable; all shapes give
  * identical chains).
  *
  * Randomness (reproducible on the CPU, see tests): walker k of chain c at global step s uses
@@ -242,8 +243,9 @@ typedef struct gf_ensemble_config {
     uint64_t seed;
     int64_t chain0;      /* global index of the first chain (RNG counter offset)    */
     int32_t mode;        /* 0 = auto; 1 = grid-wide barrier per half-step (one cooperative launch, or one
-                            launch per half-step when not co-resident); 2 = one block per chain        */
-    int32_t reserved;
+                            launch per half-step when not co-resident); 2 = one block per chain;
+                            3 = one thread-block cluster per chain, ensemble in distributed shared memory */
+    int32_t cluster_blocks; /* mode 0 / 3: CTAs per cluster (rounded up to a power of two, <= 16); 0 = auto */
 } gf_ensemble_config;
 /* d_pos [nchains][nwalkers][ndim] and d_lnp [nchains][nwalkers] are updated in place (d_lnp must hold
  * ln_prob(d_pos) on entry: call gf_lnprob first).  Optional outputs: d_chain

@@ -89,6 +89,17 @@ def eig(ham):
     return lam, vec.view(np.complex128).reshape(n, 3, 3), xf.reshape(n, 2, 2), ok.astype(bool)
 
 
+def deflate(ham):
+    """gfp_herm3_x4_deflate on Hermitian matrices: ((n, 2, 2) = |V_ai|^2 for rows e, mu and columns
+    (isolated eigenvalue, upper member of the remaining pair), status bits)."""
+    h = np.ascontiguousarray(np.asarray(ham, dtype=np.complex128)).reshape(-1, 3, 3)
+    n = h.shape[0]
+    hv = h.view(np.float64).reshape(n, 18)
+    x4, st = np.empty((n, 4)), np.empty(n, dtype=np.uint8)
+    load().hh_deflate(_p(hv), C.c_int64(n), _p(x4), _p(st))
+    return x4.reshape(n, 2, 2), st
+
+
 def ensemble(fm, pos, lnp, nsteps, nwalkers, nchains=1, nfree=None, step0=0, thin=1, a=2.0, seed=0, chain0=0):
     """Sequential host replay of gf_ensemble_run.  Returns (pos, lnp, chain, lnp_chain, naccept)."""
     ndim = fm.ndim

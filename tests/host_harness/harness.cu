@@ -96,6 +96,19 @@ extern "C" void hh_eig(const double* ham /*[n][18]*/, int64_t n, double* lam, do
     }
 }
 
+/* deflation refinement of single matrices: x4 = (|V_00|^2, |V_01|^2, |V_10|^2, |V_11|^2), status bits */
+extern "C" void hh_deflate(const double* ham /*[n][18]*/, int64_t n, double* x4 /*[n][4]*/, uint8_t* st) {
+    for (int64_t i = 0; i < n; ++i) {
+        const double* h = ham + 18 * i;
+        gfp_herm3 m;
+        m.d0 = h[0]; m.d1 = h[8]; m.d2 = h[16];
+        m.ar = h[2]; m.ai = h[3]; m.br = h[4]; m.bi = h[5]; m.cr = h[10]; m.ci = h[11];
+        gfp_x4 x = {NAN, NAN, NAN, NAN};
+        st[i] = (uint8_t)gfp_herm3_x4_deflate(m, x);
+        x4[4 * i] = x.x00; x4[4 * i + 1] = x.x01; x4[4 * i + 2] = x.x10; x4[4 * i + 3] = x.x11;
+    }
+}
+
 /* sequential replay of gf_ensemble_run: same update function, same order of half-steps */
 extern "C" int hh_ensemble(const gf_model* model, const gf_ensemble_config* cfg, double* pos, double* lnp, double* chain,
                            double* lnp_chain, unsigned long long* naccept) {

@@ -474,14 +474,15 @@ def test_device_sampler_replays_numpy_stretch_move(torch, golden):
 
 
 def test_device_sampler_many_chains_and_launch_paths(torch, golden):
-    """Batched independent chains through the three launch shapes -- one block per chain, one
-    cooperative grid launch, one launch per half-step (batch too large for co-residency) -- must give
-    identical chains, and a sub-set of chains must not depend on what else is in the batch."""
+    """Batched independent chains through the four launch shapes -- one cluster per chain (ensemble in
+    distributed shared memory), one block per chain, one cooperative grid launch, one launch per
+    half-step (batch too large for co-residency) -- must give identical chains, and a sub-set of chains
+    must not depend on what else is in the batch."""
     g = golden('ref_llh.npz')
     args, asimov, pset = models.notebook_model(g['asimov_angles'])
     fn = llh.LnProb(args, asimov, pset)
     rng = np.random.default_rng(2)
-    k, nchains, nsteps = 32, 6000, 6
+    k, nchains, nsteps = 32, 24000, 6       # 3000 blocks of 128 threads: more than 148 SMs hold at once
     p0 = models.draw_in_ranges(pset, k * nchains, rng, seeds=True).reshape(nchains, k, 6)
     p0[:, :, 4], p0[:, :, 5] = rng.uniform(.9, 1, (nchains, k)), rng.uniform(.8, 1, (nchains, k))
     lib = _lib.load()
@@ -489,11 +490,13 @@ def test_device_sampler_many_chains_and_launch_paths(torch, golden):
     before = lib.gf_launch_count()
     big.run_mcmc(p0, nsteps)
     assert lib.gf_launch_count() - before == 1 + 3 * nsteps     # scoring + (2 half-steps + 1 store) per step
-    blk = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3)            # auto: one block per chain
-    before = lib.gf_launch_count()
-    blk.run_mcmc(p0, nsteps)
-    assert lib.gf_launch_count() - before == 2                  # scoring + ONE launch
-    assert np.array_equal(blk.chain, big.chain) and np.array_equal(blk.acceptance_fraction, big.acceptance_fraction)
+    for mode in (0, 2, 3):                                      # auto (= cluster per chain), block per chain, cluster per chain
+        blk = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=3, mode=mode)
+        before = lib.gf_launch_count()
+        blk.run_mcmc(p0, nsteps)
+        assert lib.gf_launch_count() - before == 2              # scoring + ONE launch
+        assert np.array_equal(blk.chain, big.chain) and np.array_equal(blk.acceptance_fraction, big.acceptance_fraction)
+        assert np.array_equal(blk.lnprobability, big.lnprobability)
     sub = slice(4100, 4110)
     coop = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=10, seed=3, chain0=4100, mode=1)   # co-resident: cooperative launch
     before = lib.gf_launch_count()
@@ -501,15 +504,44 @@ def test_device_sampler_many_chains_and_launch_paths(torch, golden):
     assert lib.gf_launch_count() - before == 2
     assert np.array_equal(big.chain[sub], coop.chain)
     assert big.chain.shape == (nchains, k, nsteps, 6) and big.acceptance_fraction.shape == (nchains, k)
-    # block mode with several walker pairs per thread (2 x 300 > 256 threads) and a large ensemble (grid path)
-    for kk in (600, 4096):
+    # block mode with several walker pairs per thread (2 x 300 > 256 threads), clusters of every size with
+    # partly filled CTAs, and ensembles too large for a cluster (auto falls back to the grid path)
+    for kk, shapes in ((600, ((2, 0), (3, 0), (3, 2), (3, 8), (3, 16))), (4096, ((0, 0), (3, 8), (3, 16))), (10000, ((0, 0),))):
         q0 = models.draw_in_ranges(pset, kk, rng, seeds=True)
         q0[:, 4], q0[:, 5] = rng.uniform(.9, 1, kk), rng.uniform(.8, 1, kk)
-        a = mcmc.DeviceEnsembleSampler(kk, 6, fn, seed=8, mode=2 if kk == 600 else 0)
         b = mcmc.DeviceEnsembleSampler(kk, 6, fn, seed=8, mode=1)
-        a.run_mcmc(q0, 5)
         b.run_mcmc(q0, 5)
-        assert np.array_equal(a.chain, b.chain)
+        for mode, nc in shapes:
+            a = mcmc.DeviceEnsembleSampler(kk, 6, fn, seed=8, mode=mode, cluster_blocks=nc)
+            pa, la, _ = a.run_mcmc(q0, 5)
+            assert np.array_equal(a.chain, b.chain), (kk, mode, nc)
+            assert np.array_equal(pa, b.chain[:, -1]) and np.array_equal(la, b.lnprobability[:, -1])
+    with pytest.raises(ValueError):
+        mcmc.DeviceEnsembleSampler(20000, 6, fn, seed=8, mode=3).run_mcmc(models.draw_in_ranges(pset, 20000, rng, seeds=True), 1)
+
+
+def test_device_sampler_bsm_model_launch_shapes(torch, golden):
+    """The BSM log-posterior (fixed-texture specialisation, two interleaved bin chains) inside the
+    sampler: cluster, block and grid shapes give the same chain, and the stored log-posteriors are the
+    ones gf_lnprob returns for the stored positions."""
+    from golemflavor_b200.enums import Texture
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
+    fn = llh.LnProb(args, asimov, pset)
+    np.random.seed(3)
+    k = 512
+    p0 = mcmc.flat_seed(pset, k)
+    ref = mcmc.DeviceEnsembleSampler(k, fn.ndim, fn, seed=11, mode=1)
+    ref.run_mcmc(p0, 12)
+    for mode, nc in ((0, 0), (2, 0), (3, 4), (3, 16)):
+        s = mcmc.DeviceEnsembleSampler(k, fn.ndim, fn, seed=11, mode=mode, cluster_blocks=nc)
+        s.run_mcmc(p0, 12)
+        assert np.array_equal(s.chain, ref.chain), (mode, nc)
+        assert np.array_equal(s.lnprobability, ref.lnprobability)
+    assert 0.05 < ref.acceptance_fraction.mean() < 0.9
+    # same per-point code, but a separate instantiation (four interleaved bins instead of two): FMA
+    # contraction may differ in the last bits
+    assert np.allclose(fn(ref.chain[:, -1]), ref.lnprobability[:, -1], rtol=1e-11, atol=0)
 
 
 def test_mcmc_driver_uses_device_sampler_and_recovers_injection(torch, golden, capsys):

@@ -275,6 +275,47 @@ def test_harness_eigen_stage_against_lapack_on_random_bsm_points():
     assert nfast > 0.5 * 16 * n   # the closed-form path must carry the bulk of the points
 
 
+def test_harness_deflation_refinement_on_near_degenerate_pairs():
+    """gfp_herm3_x4_deflate (the fallback of the energy-bin loop) against mpmath on Hermitian matrices with
+    a prescribed eigenvalue pair splitting from 1e-2 down to 1e-9 of the spectral scale: |V_ai|^2 to
+    ~eps / gap (the conditioning of the eigenvectors themselves), at every matrix scale the pencil reaches."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+    worst = {}
+    for gap in (1e-2, 1e-4, 1e-6, 1e-9):
+        hams, truth_x = [], []
+        for trial in range(12):
+            z = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+            q, _ = np.linalg.qr(z)
+            top = rng.choice([-1.0, 1.0])                      # isolated eigenvalue above or below the pair
+            lam = np.array([top * 1.0, -0.5 * top + gap, -0.5 * top - gap]) * rng.uniform(0.3, 3.0) + rng.uniform(-2, 2)
+            scale = 10.0 ** rng.uniform(-30, 30)
+            h = (q * lam) @ q.conj().T * scale
+            h = (h + h.conj().T) / 2
+            hams.append(h)
+            hm = mp.matrix(3, 3)
+            for a in range(3):
+                for b in range(3):
+                    hm[a, b] = mp.mpc(float(h[a, b].real), float(h[a, b].imag)) if a != b else mp.mpf(float(h[a, a].real))
+            ev, vec = mp.eighe(hm)
+            ev = [float(e) for e in ev]
+            iso = 0 if abs(ev[0] - ev[1]) > abs(ev[1] - ev[2]) else 2     # sorted ascending: the pair is adjacent
+            upper = 2 if iso == 0 else 1
+            truth_x.append([[float(abs(vec[a, iso]) ** 2), float(abs(vec[a, upper]) ** 2)] for a in range(2)])
+        x, st = hh.deflate(np.array(hams))
+        assert np.all(st & _lib.ST_REFINED) and not np.any(st & _lib.ST_NON_FINITE)
+        worst[gap] = float(np.abs(x - np.array(truth_x)).max())
+        assert worst[gap] < 4e-15 / gap + 1e-14, worst
+        assert np.all(((st & _lib.ST_ILL_COND) != 0) == (gap < 1e-7))      # relative gap below 1e-6 is flagged
+    # exactly degenerate pair: flagged, and the (arbitrary) split of the pair stays a valid one
+    x, st = hh.deflate(np.diag([2.0, -1.0, -1.0]).astype(complex)[None])
+    assert (st[0] & _lib.ST_ILL_COND) and np.allclose(x[0, 0], [1.0, 0.0], atol=1e-15) and abs(x[0, 1, 0]) < 1e-15 and 0.0 <= x[0, 1, 1] <= 1.0
+    # zero / non-finite matrices hand over to Jacobi
+    _, st = hh.deflate(np.zeros((1, 3, 3), dtype=complex))
+    assert st[0] & _lib.ST_NON_FINITE
+
+
 def test_harness_prior_draws_follow_philox_convention():
     fm = scan.scan_model('unitary')
     th = hh.draw(fm, 26, 12345, 1000)
