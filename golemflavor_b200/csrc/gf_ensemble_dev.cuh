@@ -35,9 +35,14 @@ struct gf_ens_args {
 };
 
 /* The three Philox words of one update (see gf_ensemble_config): stretch factor z, partner index j in
- * the other half, and the uniform of the acceptance test. */
+ * the other half, and the uniform of the acceptance test.
+ *
+ * Latency matters more than throughput here (about one warp per SM sub-partition, in-order issue): the
+ * update is written so that the partner's coordinates are REQUESTED first -- all dimensions back to back,
+ * not one round trip per dimension -- and the division and the two logarithms execute while they are in
+ * flight. */
 struct gf_ens_draw {
-    double z, u_accept;
+    double u_z, u_accept;
     int j;
 };
 
@@ -45,26 +50,53 @@ GF_HD gf_ens_draw gf_ens_draws(const gf_ens_args& A, uint64_t gid, int64_t step,
     const uint64_t s = (uint64_t)step;
     const gf_u4 r = gf_philox4x32_10((uint32_t)gid, (uint32_t)s, (uint32_t)(s >> 32), 0u, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
     gf_ens_draw d;
-    /* no FMA contraction in the proposal: bit-reproducible with NumPy */
-    const double t = GF_ADD_RN(GF_MUL_RN(A.a - 1.0, gf_u01(r.x)), 1.0);
-    d.z = GF_DIV_RN(GF_MUL_RN(t, t), A.a);
+    d.u_z = gf_u01(r.x);
     int j = (int)(gf_u01(r.y) * (double)half);
     d.j = j < half ? j : half - 1;
     d.u_accept = gf_u01(r.z);
     return d;
 }
 
+/* z = ((a-1) u + 1)^2 / a without FMA contraction: bit-reproducible with NumPy.  Dividing by a power of
+ * two (emcee's default a = 2) is an exact multiplication. */
+GF_HD double gf_ens_z(const gf_ens_args& A, double u) {
+    const double t = GF_ADD_RN(GF_MUL_RN(A.a - 1.0, u), 1.0);
+    const double tt = GF_MUL_RN(t, t);
+    return A.a == 2.0 ? GF_MUL_RN(tt, 0.5) : GF_DIV_RN(tt, A.a);
+}
+
 /* q = c_j - z (c_j - p), contraction-free */
 GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(cd, GF_MUL_RN(z, GF_SUB_RN(cd, pd))); }
 
-/* score the proposal q and decide: accept iff (nfree-1) ln z + lnp(q) - lnp(p) > ln u (false for NaN) */
-template <int SPEC, int ILP>
-GF_HD bool gf_ens_accept(const gf_dev_model& m, const gf_ens_args& A, const gf_ens_draw& dr, const double* q, double lold, double& lnew) {
+/*
+ * One stretch-move update given accessors for the partner's and the walker's own coordinates
+ * (global memory through L2, or distributed shared memory).  Returns true and leaves the proposal in q /
+ * its log-posterior in lnew when the move is accepted: accept iff (nfree-1) ln z + lnp(q) - lnp(p) > ln u
+ * (false for NaN).
+ */
+template <int SPEC, int ILP, class LoadPartner, class LoadOwn>
+GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, const gf_ens_draw& dr, LoadPartner partner, LoadOwn own, double lold,
+                       double* q, double& lnew) {
+    const int ndim = m.ndim;
+    double cv[GF_MAX_DIM], pv[GF_MAX_DIM];
+#pragma unroll
+    for (int d = 0; d < GF_MAX_DIM; ++d) {
+        if (d < ndim) {
+            cv[d] = partner(d);
+            pv[d] = own(d);
+        }
+    }
+    const double z = gf_ens_z(A, dr.u_z);
+    const double lz = (double)(A.nfree - 1) * log(z);
+    const double lu = log(dr.u_accept);
+#pragma unroll
+    for (int d = 0; d < GF_MAX_DIM; ++d)
+        if (d < ndim) q[d] = gf_ens_stretch(cv[d], pv[d], z);
     double fr[3];
     unsigned st = 0u;
     lnew = gf_point_lnprob<SPEC, ILP>(m, [&](int d) { return q[d]; }, fr, st);
-    const double diff = (double)(A.nfree - 1) * log(dr.z) + lnew - lold;
-    return diff > log(dr.u_accept);
+    const double diff = lz + lnew - lold;
+    return diff > lu;
 }
 
 /* one stretch-move update of walker k (in half h) of chain c, positions in global memory */
@@ -73,17 +105,16 @@ GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_
     const int ndim = m.ndim, half = A.nwalkers / 2;
     const uint64_t gid = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)k;
     const gf_ens_draw dr = gf_ens_draws(A, gid, step, half);
-    const double* p = A.pos + (c * A.nwalkers + k) * ndim;
+    double* p = A.pos + (c * A.nwalkers + k) * ndim;
     const double* cj = A.pos + (c * A.nwalkers + (1 - h) * half + dr.j) * ndim;
     double q[GF_MAX_DIM];
+    double lnew;
     /* positions of other walkers were written by other SMs before the last grid barrier: read them
      * through L2 (ld.global.cg), not through this SM's non-coherent L1 */
-    for (int d = 0; d < ndim; ++d) q[d] = gf_ens_stretch(GF_LDCG(cj + d), GF_LDCG(p + d), dr.z);
-    double lnew;
-    const bool accept = gf_ens_accept<SPEC, ILP>(m, A, dr, q, GF_LDCG(A.lnp + c * A.nwalkers + k), lnew);
+    const bool accept = gf_ens_move<SPEC, ILP>(
+        m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew);
     if (accept) {
-        double* pw = A.pos + (c * A.nwalkers + k) * ndim;
-        for (int d = 0; d < ndim; ++d) pw[d] = q[d];
+        for (int d = 0; d < ndim; ++d) p[d] = q[d];
         A.lnp[c * A.nwalkers + k] = lnew;
     }
     return accept ? 1u : 0u;

@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(GF_LP_THREADS, SPEC == GF_SPEC_SM ? 16 : GF_LP
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    auto get = [&](int k) { return __ldg(th.p + i * th.ld_point + (int64_t)k * th.ld_dim); };
+    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform) */
+    const double* __restrict__ row = th.p + i * th.ld_point;
+    auto get = [&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); };
     if (KIND == GF_K_LNPRIOR) {
         lnp[i] = gf_point_lnprior(m, get);
         return;

@@ -585,7 +585,7 @@ GF_HD gfp_herm3 gfp_herm_from_cols(const gfp_cols12& u, double m1, double m2) {
 
 /* (sin^4 phi, cos 2psi) -> (f_e, f_mu, f_tau); fr.py:101-113 with sin^2(acos(c)/2) = (1-c)/2. */
 GF_HD void gfp_angles_to_fr(double sphi4, double c2psi, double* f) {
-    const double sphi2 = sqrt(sphi4);
+    const double sphi2 = gfp_sqrt01(sphi4);
     const double cphi2 = 1.0 - sphi2;
     double spsi2 = 0.5 * (1.0 - c2psi);
     if (!(fabs(c2psi) <= 1.0)) spsi2 = NAN; /* acos domain of the reference */
