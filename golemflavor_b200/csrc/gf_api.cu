@@ -363,7 +363,28 @@ __global__ void __launch_bounds__(GF_EW_THREADS) k_selftest_math(const double* _
     rc[i] = gfp_rcp(x[i]);
 }
 
+__global__ void __launch_bounds__(GF_EW_THREADS)
+    k_selftest_trig(const double* __restrict__ x, int64_t n, double* __restrict__ sn, double* __restrict__ cs, double* __restrict__ cs_only) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s, c;
+    gfp_sincos(x[i], &s, &c);
+    sn[i] = s;
+    cs[i] = c;
+    cs_only[i] = gfp_cos(x[i]);
+}
+
 /* ------------------------------------------------------------------ C ABI */
+
+extern "C" int gf_selftest_trig(const double* d_x, int64_t n, double* d_sin, double* d_cos, double* d_cos_only, void* stream) {
+    GF_REQUIRE(n >= 0, "gf_selftest_trig: n = %lld", (long long)n);
+    if (n == 0) return GF_OK;
+    GF_REQUIRE(d_x && d_sin && d_cos && d_cos_only, "gf_selftest_trig: null pointer");
+    k_selftest_trig<<<gf_blocks_for(n, GF_EW_THREADS), GF_EW_THREADS, 0, (cudaStream_t)stream>>>(d_x, n, d_sin, d_cos, d_cos_only);
+    ++g_gf_launches;
+    GF_LAUNCH_CHECK("k_selftest_trig");
+    return GF_OK;
+}
 
 extern "C" int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* d_rcp_out, void* stream) {
     GF_REQUIRE(n >= 0, "gf_selftest_math: n = %lld", (long long)n);

@@ -157,12 +157,18 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
 #else
 #define GF_TICK(var)
 #endif
+    /* software pipeline: the draws of the NEXT half-step (Philox, stretch factor, both logarithms -- nothing
+     * that depends on a walker position) are computed between the arrive and the wait of the cluster barrier */
+    gf_ens_draw dr;
+    if (active) {
+        dr = gf_ens_draws(A, gid0, A.step0, half);
+        gf_ens_finish_draw(A, dr);
+    }
+    GF_TICK(t_draw)
     for (int64_t s = 0; s < A.nsteps; ++s) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             if (active) {
-                const gf_ens_draw dr = gf_ens_draws(A, gid0 + (uint64_t)(h * half), A.step0 + s, half);
-                GF_TICK(t_draw)
                 /* j / T for j < 4096, T <= 256: (j + 1/2) / T stays >= 1/512 away from every integer, so the
                  * approximate fp32 quotient truncates to the exact floor (an integer division costs ~150 cycles) */
                 const int rj = __float2int_rz(__fdividef((float)dr.j + 0.5f, (float)T)), jl = dr.j - rj * T;
@@ -170,7 +176,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 double* p = pos_s + (h * T + wl) * ndim;
                 double q[GF_MAX_DIM];
                 double lnew;
-                if (gf_ens_move<SPEC, ILP>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; }, lnp_s[h * T + wl], q, lnew)) {
+                if (gf_ens_move<SPEC, ILP, true>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; }, lnp_s[h * T + wl], q, lnew)) {
                     for (int d = 0; d < ndim; ++d) p[d] = q[d];
                     lnp_s[h * T + wl] = lnew;
                     acc0 += h ? 0u : 1u;
@@ -178,7 +184,13 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 }
                 GF_TICK(t_eval)
             }
-            cluster.sync();
+            cluster.barrier_arrive();
+            if (active) { /* next half-step: (s, 1) after (s, 0), (s + 1, 0) after (s, 1) */
+                dr = gf_ens_draws(A, gid0 + (uint64_t)((1 - h) * half), A.step0 + s + h, half);
+                gf_ens_finish_draw(A, dr);
+                GF_TICK(t_draw)
+            }
+            cluster.barrier_wait();
             GF_TICK(t_sync)
         }
         if (active && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) {

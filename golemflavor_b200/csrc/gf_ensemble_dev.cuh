@@ -44,6 +44,7 @@ struct gf_ens_args {
 struct gf_ens_draw {
     double u_z, u_accept;
     int j;
+    double z, lz, lu; /* filled by gf_ens_finish_draw: stretch factor, (nfree-1) ln z, ln u_accept */
 };
 
 GF_HD gf_ens_draw gf_ens_draws(const gf_ens_args& A, uint64_t gid, int64_t step, int half) {
@@ -65,6 +66,13 @@ GF_HD double gf_ens_z(const gf_ens_args& A, double u) {
     return A.a == 2.0 ? GF_MUL_RN(tt, 0.5) : GF_DIV_RN(tt, A.a);
 }
 
+/* the arithmetic on the draws that does not depend on any walker position */
+GF_HD void gf_ens_finish_draw(const gf_ens_args& A, gf_ens_draw& dr) {
+    dr.z = gf_ens_z(A, dr.u_z);
+    dr.lz = (double)(A.nfree - 1) * log(dr.z);
+    dr.lu = log(dr.u_accept);
+}
+
 /* q = c_j - z (c_j - p), contraction-free */
 GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(cd, GF_MUL_RN(z, GF_SUB_RN(cd, pd))); }
 
@@ -72,10 +80,11 @@ GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(c
  * One stretch-move update given accessors for the partner's and the walker's own coordinates
  * (global memory through L2, or distributed shared memory).  Returns true and leaves the proposal in q /
  * its log-posterior in lnew when the move is accepted: accept iff (nfree-1) ln z + lnp(q) - lnp(p) > ln u
- * (false for NaN).
+ * (false for NaN).  FINISHED: gf_ens_finish_draw has already run (the cluster kernel does it in the shadow
+ * of the barrier); otherwise it runs here, in the shadow of the loads.
  */
-template <int SPEC, int ILP, class LoadPartner, class LoadOwn>
-GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, const gf_ens_draw& dr, LoadPartner partner, LoadOwn own, double lold,
+template <int SPEC, int ILP, bool FINISHED, class LoadPartner, class LoadOwn>
+GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw& dr, LoadPartner partner, LoadOwn own, double lold,
                        double* q, double& lnew) {
     const int ndim = m.ndim;
     double cv[GF_MAX_DIM], pv[GF_MAX_DIM];
@@ -86,17 +95,15 @@ GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, const gf_ens
             pv[d] = own(d);
         }
     }
-    const double z = gf_ens_z(A, dr.u_z);
-    const double lz = (double)(A.nfree - 1) * log(z);
-    const double lu = log(dr.u_accept);
+    if (!FINISHED) gf_ens_finish_draw(A, dr);
 #pragma unroll
     for (int d = 0; d < GF_MAX_DIM; ++d)
-        if (d < ndim) q[d] = gf_ens_stretch(cv[d], pv[d], z);
+        if (d < ndim) q[d] = gf_ens_stretch(cv[d], pv[d], dr.z);
     double fr[3];
     unsigned st = 0u;
     lnew = gf_point_lnprob<SPEC, ILP>(m, [&](int d) { return q[d]; }, fr, st);
-    const double diff = lz + lnew - lold;
-    return diff > lu;
+    const double diff = dr.lz + lnew - lold;
+    return diff > dr.lu;
 }
 
 /* one stretch-move update of walker k (in half h) of chain c, positions in global memory */
@@ -104,14 +111,14 @@ template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int h, int64_t step) {
     const int ndim = m.ndim, half = A.nwalkers / 2;
     const uint64_t gid = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)k;
-    const gf_ens_draw dr = gf_ens_draws(A, gid, step, half);
+    gf_ens_draw dr = gf_ens_draws(A, gid, step, half);
     double* p = A.pos + (c * A.nwalkers + k) * ndim;
     const double* cj = A.pos + (c * A.nwalkers + (1 - h) * half + dr.j) * ndim;
     double q[GF_MAX_DIM];
     double lnew;
     /* positions of other walkers were written by other SMs before the last grid barrier: read them
      * through L2 (ld.global.cg), not through this SM's non-coherent L1 */
-    const bool accept = gf_ens_move<SPEC, ILP>(
+    const bool accept = gf_ens_move<SPEC, ILP, false>(
         m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew);
     if (accept) {
         for (int d = 0; d < ndim; ++d) p[d] = q[d];

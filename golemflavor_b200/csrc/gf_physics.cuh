@@ -92,6 +92,85 @@ GF_HD double gfp_sqrt01(double x) {
     return sqrt(x);
 }
 
+/*
+ * sin / cos of the CP phase.  The library routines fetch their polynomial coefficients from a table in
+ * global memory (LDG): harmless in the throughput kernels, but a ~300-cycle stall on the critical path of
+ * the ensemble sampler, which runs about one warp per SM.  Same algorithm with immediate coefficients:
+ * Cody-Waite reduction by pi/2 in three parts, then the fdlibm minimax polynomials on [-pi/4, pi/4]
+ * (|error| < 1 ulp of the result scale).  |x| >= 1e5 or non-finite arguments -- never inside a prior box --
+ * take the library routine.
+ */
+#define GFP_S1 -1.66666666666666324348e-01
+#define GFP_S2 8.33333333332248946124e-03
+#define GFP_S3 -1.98412698298579493134e-04
+#define GFP_S4 2.75573137070700676789e-06
+#define GFP_S5 -2.50507602534068634195e-08
+#define GFP_S6 1.58969099521155010221e-10
+#define GFP_C1 4.16666666666666019037e-02
+#define GFP_C2 -1.38888888888741095749e-03
+#define GFP_C3 2.48015872894767294178e-05
+#define GFP_C4 -2.75573143513906633035e-07
+#define GFP_C5 2.08757232129817482790e-09
+#define GFP_C6 -1.13596475577881948265e-11
+
+#ifdef __CUDA_ARCH__
+/* r = x - k pi/2 with k = rint(x 2/pi); returns k */
+__device__ __forceinline__ int gfp_reduce_pio2(double x, double& r) {
+    const double kd = rint(x * 0.63661977236758138);
+    r = fma(kd, -__longlong_as_double(0x3ff921fb54442d18ll), x); /* pi/2 = 1.5707963267948966 + 6.123233995736757e-17 */
+    r = fma(kd, -__longlong_as_double(0x3c91a62633145c00ll), r); /*        + 8.478427660368898e-32 (three-part split) */
+    r = fma(kd, -__longlong_as_double(0x397b839a252049c0ll), r);
+    return (int)kd;
+}
+#endif
+
+GF_HD void gfp_sincos(double x, double* sn, double* cs) {
+#ifdef __CUDA_ARCH__
+    if (!(fabs(x) < 1e5)) {
+        sincos(x, sn, cs);
+        return;
+    }
+    double r;
+    const int k = gfp_reduce_pio2(x, r);
+    const double z = r * r;
+    const double ps = fma(fma(fma(fma(fma(GFP_S6, z, GFP_S5), z, GFP_S4), z, GFP_S3), z, GFP_S2), z, GFP_S1);
+    const double pc = fma(fma(fma(fma(fma(GFP_C6, z, GFP_C5), z, GFP_C4), z, GFP_C3), z, GFP_C2), z, GFP_C1);
+    const double s = fma(r * z, ps, r);
+    const double c = fma(z, fma(z, pc, -0.5), 1.0);
+    /* quadrant: (sin, cos)(x) = (s, c), (c, -s), (-s, -c), (-c, s) for k mod 4 = 0..3 */
+    const double a = (k & 1) ? c : s, b = (k & 1) ? s : c;
+    *sn = (k & 2) ? -a : a;
+    *cs = ((k + 1) & 2) ? -b : b;
+#else
+    *sn = sin(x);
+    *cs = cos(x);
+#endif
+}
+
+GF_HD double gfp_cos(double x) {
+#ifdef __CUDA_ARCH__
+    if (!(fabs(x) < 1e5)) return cos(x);
+    double r;
+    const int k = gfp_reduce_pio2(x, r);
+    const double z = r * r;
+    /* one Horner chain with the coefficients selected by the quadrant parity:
+     * even k: cos r = 1 + z (-1/2 + z (C1 + ... + z C6));  odd k: sin r = r + r z (S1 + ... + z S6) */
+    const bool odd = k & 1;
+    double p = odd ? 0.0 : GFP_C6;
+    p = fma(p, z, odd ? GFP_S6 : GFP_C5);
+    p = fma(p, z, odd ? GFP_S5 : GFP_C4);
+    p = fma(p, z, odd ? GFP_S4 : GFP_C3);
+    p = fma(p, z, odd ? GFP_S3 : GFP_C2);
+    p = fma(p, z, odd ? GFP_S2 : GFP_C1);
+    p = fma(p, z, odd ? GFP_S1 : -0.5);
+    const double v = fma(odd ? r * z : z, p, odd ? r : 1.0);
+    /* cos x = c, -s, -c, s for k mod 4 = 0..3 */
+    return ((k + 1) & 2) ? -v : v;
+#else
+    return cos(x);
+#endif
+}
+
 /* ------------------------------------------------------------------ 3x3 Hermitian */
 
 /* Hermitian matrix: real diagonal d0,d1,d2 and the upper triangle a = H01, b = H02, c = H12. */
@@ -487,12 +566,7 @@ GF_HD gfp_trig gfp_angles_trig(double s12_2, double c13_4, double s23_2, double 
     t.s13 = gfp_sqrt01(1.0 - c13_2);
     t.s23 = gfp_sqrt01(s23_2);
     t.c23 = gfp_sqrt01(1.0 - s23_2);
-#ifdef __CUDA_ARCH__
-    sincos(dcp, &t.sd, &t.cd);
-#else
-    t.sd = sin(dcp);
-    t.cd = cos(dcp);
-#endif
+    gfp_sincos(dcp, &t.sd, &t.cd);
     return t;
 }
 
@@ -553,7 +627,7 @@ GF_HD void gfp_pmns_abs2_coords(double s12_2, double c13_4, double s23_2, double
      * negative coordinate makes the product's root NaN exactly where the reference's sqrt is NaN */
     const bool valid = s12_2 >= 0.0 && c12_2 >= 0.0 && s23_2 >= 0.0 && c23_2 >= 0.0 && s13_2 >= 0.0;
     const double prod = (c23_2 * s23_2) * (s12_2 * c12_2) * s13_2;
-    const double cross = valid ? 2.0 * gfp_sqrt01(prod) * cos(dcp) : NAN;
+    const double cross = valid ? 2.0 * gfp_sqrt01(prod) * gfp_cos(dcp) : NAN;
     X[0] = c13_2 * c12_2;
     X[1] = c13_2 * s12_2;
     X[2] = s13_2;

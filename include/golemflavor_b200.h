@@ -264,6 +264,9 @@ int gf_fp64_peak_probe(int32_t mode, int64_t iters, double* d_sink /*[>= 1]*/, d
 /* Device self-test of the MUFU-seeded helpers of the eigen stage: rsqrt_out[i] ~ 1/sqrt(x[i]),
  * rcp_out[i] ~ 1/x[i] for normal positive x (tests/test_gpu_parity.py checks them to 1e-15). */
 int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* d_rcp_out, void* stream);
+/* Device self-test of the table-free sin / cos of the CP phase (fr.py:157-159 evaluates them with NumPy):
+ * sin_out, cos_out from the joint routine, cos_only_out from the cosine-only one. */
+int gf_selftest_trig(const double* d_x, int64_t n, double* d_sin_out, double* d_cos_out, double* d_cos_only_out, void* stream);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t gf_launch_count(void);
 

@@ -58,6 +58,27 @@ def test_device_math_helpers(torch):
     assert np.max(np.abs(rc.cpu().numpy() * xl - 1)) < 1e-15
 
 
+def test_device_trig_helpers(torch):
+    """The table-free sin / cos of the CP phase (Cody-Waite reduction + fdlibm polynomials with immediate
+    coefficients) against x87 long-double NumPy: below 2 ulp of the unit scale on the prior box and far
+    around it, library fallback for huge and non-finite arguments."""
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(0, 2 * np.pi, 400000), rng.uniform(-1000, 1000, 200000), rng.uniform(-99999, 99999, 100000),
+                        np.arange(-64, 65) * (np.pi / 4), np.arange(-64, 65) * (np.pi / 2), [0.0, -0.0, 1e-300, 1e5, -1e5, 3e8, -7e15, 1e300]])
+    xt = torch.as_tensor(x).cuda()
+    sn, cs, co = torch.empty_like(xt), torch.empty_like(xt), torch.empty_like(xt)
+    _lib.check(_lib.load().gf_selftest_trig(_lib.ptr(xt), len(x), _lib.ptr(sn), _lib.ptr(cs), _lib.ptr(co), _lib.stream_ptr(torch)))
+    xl = x.astype(np.longdouble)
+    small = np.abs(x) < 1e5
+    assert np.max(np.abs(sn.cpu().numpy()[small] - np.sin(xl[small]))) < 4.5e-16
+    assert np.max(np.abs(cs.cpu().numpy()[small] - np.cos(xl[small]))) < 4.5e-16
+    assert np.max(np.abs(co.cpu().numpy()[small] - np.cos(xl[small]))) < 4.5e-16
+    assert np.allclose(sn.cpu().numpy()[~small], np.sin(x[~small]), atol=1e-15) and np.allclose(co.cpu().numpy()[~small], np.cos(x[~small]), atol=1e-15)
+    bad = torch.as_tensor(np.array([np.nan, np.inf, -np.inf])).cuda()
+    _lib.check(_lib.load().gf_selftest_trig(_lib.ptr(bad), 3, _lib.ptr(sn), _lib.ptr(cs), _lib.ptr(co), _lib.stream_ptr(torch)))
+    assert np.all(np.isnan(sn.cpu().numpy()[:3])) and np.all(np.isnan(cs.cpu().numpy()[:3])) and np.all(np.isnan(co.cpu().numpy()[:3]))
+
+
 # ------------------------------------------------------------------ docstring known answers (fr.py)
 def test_kat_angles_to_u(torch):
     ref = np.array([[0.66195018 + 0.j, 0.33097509 + 0.j, 0.04757188 - 0.6708311j],
