@@ -37,8 +37,35 @@ __global__ void __launch_bounds__(GF_LP_THREADS, SPEC == GF_SPEC_SM ? 16 : GF_LP
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform) */
     const double* __restrict__ row = th.p + i * th.ld_point;
+    if (SPEC == GF_SPEC_SM && KIND != GF_K_LNPRIOR) {
+        /* SM-only models are bound by instruction issue, and a third of their instructions were 64-bit
+         * address arithmetic of theta reads through the runtime column map (every value is read twice: by
+         * the prior loop and by the physics).  Stage the point's row ONCE in shared memory, column-major
+         * per block (each thread reads back only what it wrote: no barrier, no bank conflicts); a read is
+         * then one LDS at a warp-uniform offset. */
+        extern __shared__ double sh_theta[];
+        const double* src = row;
+        for (int k = 0; k < m.ndim; ++k, src += th.ld_dim) sh_theta[k * GF_LP_THREADS + threadIdx.x] = __ldg(src);
+        auto get = [&](int k) { return sh_theta[k * GF_LP_THREADS + threadIdx.x]; };
+        double fr[3];
+        unsigned st = 0u;
+        if (KIND == GF_K_FR) {
+            gf_point q;
+            gf_resolve_point<SPEC>(m, get, q);
+            st = gf_point_fr<SPEC, 1>(m, q, fr);
+        } else {
+            lnp[i] = gf_point_lnprob<SPEC, 1>(m, get, fr, st);
+        }
+        if (fr_out) {
+            fr_out[3 * i] = fr[0];
+            fr_out[3 * i + 1] = fr[1];
+            fr_out[3 * i + 2] = fr[2];
+        }
+        if (status) status[i] = (uint8_t)st;
+        return;
+    }
+    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform) */
     auto get = [&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); };
     if (KIND == GF_K_LNPRIOR) {
         lnp[i] = gf_point_lnprior(m, get);
@@ -82,7 +109,7 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
     if (spec == GF_SPEC_FIXED)
         k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else if (spec == GF_SPEC_SM)
-        k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+        k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, (size_t)d.ndim * GF_LP_THREADS * sizeof(double), stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else
         k_lnprob<KIND, GF_SPEC_GENERIC><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     ++g_gf_launches;
@@ -218,7 +245,7 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
             k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else if (spec == GF_SPEC_SM)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
+            k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, (size_t)ndim * GF_LP_THREADS * sizeof(double), p.stream[s]>>>(
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else
             k_lnprob<GF_K_LNPROB, GF_SPEC_GENERIC><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
