@@ -541,6 +541,37 @@ def test_device_sampler_many_chains_and_launch_paths(torch, golden):
         mcmc.DeviceEnsembleSampler(20000, 6, fn, seed=8, mode=3).run_mcmc(models.draw_in_ranges(pset, 20000, rng, seeds=True), 1)
 
 
+def test_device_sampler_thinning_small_ensembles_and_continuation(torch, golden):
+    """Edge shapes of the device sampler in every launch shape: thinning with a step count that is not a
+    multiple of the stride, the smallest ensemble emcee allows (2 ndim walkers), non-power-of-two half-ensembles, several
+    chains, no stored log-posterior, and continuation of a run (global step counter) -- all compared with a
+    single unthinned cooperative-grid run."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(4)
+    for k, nchains in ((12, 3), (14, 2), (70, 5), (514, 1)):     # emcee rule: at least 2 ndim walkers
+        p0 = models.draw_in_ranges(pset, k * nchains, rng, seeds=True).reshape(nchains, k, 6)
+        p0[:, :, 4], p0[:, :, 5] = rng.uniform(.9, 1, (nchains, k)), rng.uniform(.8, 1, (nchains, k))
+        up = (lambda x: x) if nchains > 1 else (lambda x: x[None])      # one chain: the sampler drops the chain axis
+        full = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=9, mode=1)
+        full.run_mcmc(p0 if nchains > 1 else p0[0], 23)
+        fc, fl = up(full.chain), up(full.lnprobability)
+        for mode in (0, 2, 3):
+            s = mcmc.DeviceEnsembleSampler(k, 6, fn, nchains=nchains, seed=9, mode=mode, store_lnprob=(mode != 2))
+            s.run_mcmc(p0 if nchains > 1 else p0[0], 10, thin=3)   # stores steps 3, 6, 9
+            s.run_mcmc(None, 13, thin=1)                             # continues at global step 10
+            sc = up(s.chain)
+            assert sc.shape == (nchains, k, 3 + 13, 6)
+            assert np.array_equal(sc[:, :, :3], fc[:, :, 2:10:3]), (k, mode)
+            assert np.array_equal(sc[:, :, 3:], fc[:, :, 10:]), (k, mode)
+            assert np.array_equal(s.acceptance_fraction, full.acceptance_fraction)
+            if mode != 2:
+                assert np.array_equal(up(s.lnprobability)[:, :, 3:], fl[:, :, 10:])
+    with pytest.raises(ValueError):
+        mcmc.DeviceEnsembleSampler(7, 6, fn, seed=1).run_mcmc(models.draw_in_ranges(pset, 7, rng, seeds=True), 1)   # odd ensemble
+
+
 def test_device_sampler_bsm_model_launch_shapes(torch, golden):
     """The BSM log-posterior (fixed-texture specialisation, two interleaved bin chains) inside the
     sampler: cluster, block and grid shapes give the same chain, and the stored log-posteriors are the
