@@ -243,7 +243,12 @@ template <class Get>
 GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
     double acc = 0.0;
     bool inside = true;
-    for (int k = 0; k < m.ndim; ++k) {
+    /* fully unrolled with an early exit on the (warp-uniform) dimension count: with a compile-time k the
+     * prior tables are constant-bank operands of the compares and the FMA instead of indexed constant
+     * loads -- the rolled loop was 21 % of the instructions of the SM-only kernel */
+#pragma unroll
+    for (int k = 0; k < GF_MAX_DIM; ++k) {
+        if (k >= m.ndim) break;
         const double v = get(k);
         inside = inside && (v >= m.lo[k]) && (v <= m.hi[k]);
         const double z = (v - m.mu[k]) * m.inv_sigma[k];
