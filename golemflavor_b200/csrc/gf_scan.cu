@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_S
         double fr[3];
         if (SCAN) {
             double theta[GF_MAX_DIM];
-            gf_draw_theta(m, seed, first_index + j, theta);
+            gf_draw_theta<SPEC == GF_SPEC_SM>(m, seed, first_index + j, theta);
             gf_point q;
             gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
             gf_point_fr<SPEC, GF_SCAN_ILP_FOR(SPEC)>(m, q, fr);

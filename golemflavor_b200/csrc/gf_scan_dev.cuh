@@ -49,10 +49,28 @@ GF_HD double gf_draw_dim(const gf_dev_model& m, int k, double u) {
     return fmin(fmax(x, m.lo[k]), m.hi[k]);
 }
 
+/* UNROLL: fully unrolled with an early exit on the (uniform) dimension count -- with a compile-time k the
+ * prior tables are constant-bank operands and the word of the Philox block is a register, not a select
+ * chain: +12 % on the unitary scan, +8 % on the x scan.  The BSM scan kernels keep the rolled loop: they sit
+ * at the 128-register limit and the unrolled draws made them spill. */
+template <bool UNROLL = false>
 GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, double* theta) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
     gf_u4 r = {0u, 0u, 0u, 0u};
+    if (UNROLL) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < GF_MAX_DIM; ++k) {
+            if (k >= m.ndim) break;
+            const int j = k & 3;
+            if (j == 0) r = gf_philox4x32_10(c0, c1, (uint32_t)(k >> 2), 0u, k0, k1);
+            const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
+            theta[k] = gf_draw_dim(m, k, gf_u01(w));
+        }
+        return;
+    }
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
