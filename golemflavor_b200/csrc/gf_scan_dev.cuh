@@ -58,7 +58,7 @@ GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, d
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
     gf_u4 r = {0u, 0u, 0u, 0u};
-    if (UNROLL) {
+    if constexpr (UNROLL) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
@@ -69,16 +69,16 @@ GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, d
             const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
             theta[k] = gf_draw_dim(m, k, gf_u01(w));
         }
-        return;
-    }
+    } else {
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-    for (int k = 0; k < m.ndim; ++k) {
-        const int j = k & 3;
-        if (j == 0) r = gf_philox4x32_10(c0, c1, (uint32_t)(k >> 2), 0u, k0, k1);
-        const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
-        theta[k] = gf_draw_dim(m, k, gf_u01(w));
+        for (int k = 0; k < m.ndim; ++k) {
+            const int j = k & 3;
+            if (j == 0) r = gf_philox4x32_10(c0, c1, (uint32_t)(k >> 2), 0u, k0, k1);
+            const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;
+            theta[k] = gf_draw_dim(m, k, gf_u01(w));
+        }
     }
 }
 
