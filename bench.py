@@ -335,6 +335,15 @@ def run_gpu(opts):
         cfg_info['C2_emcee_sm_fit'] = {'walkers': 1024, 'steps': 10000, 'ndim': 6, 'seconds': sec, 'evals_per_s': 1024 * 1e4 / sec,
                                        'acceptance': float(np.mean(smp.acceptance_fraction)), 'launches': 1,
                                        'note': 'replicas only: every rank runs the same chain shape independently'}
+        # C1: the reference's own CPU-sized case (3 raw source ratios, fixed NuFIT PMNS), here on the device sampler
+        a1, as1, ps1 = _m.sm_fit_c1(g['asimov_angles'])
+        f1 = llh.LnProb(a1, as1, ps1)
+        p1 = mcmc.flat_seed(ps1, 100)
+        smp1 = mcmc.DeviceEnsembleSampler(100, 3, f1, seed=25)
+        smp1.run_mcmc(p1, 100, store=False)
+        sec, _ = timed(lambda: smp1.run_mcmc(None, 1000, store=True, return_tensor=True))
+        cfg_info['C1_sm_fit_fixed_pmns'] = {'walkers': 100, 'steps': 1000, 'ndim': 3, 'seconds': sec, 'evals_per_s': 100 * 1000 / sec,
+                                            'acceptance': float(np.mean(smp1.acceptance_fraction)), 'launches': 1}
         p3 = mcmc.flat_seed(pset, 4096)
         smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
         smp3.run_mcmc(p3, 100, store=False)
