@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
  */
 /* threads per CTA: 256 for the register-light SM-only models, 128 for the BSM path (full register file
  * for the eigen stage: no spills on the latency-critical path) */
-#define GF_ENS_CL_MAX_THREADS(SPEC) ((SPEC) == GF_SPEC_SM ? 256 : 128)
+#define GF_ENS_CL_MAX_THREADS(SPEC) (GF_SPEC_IS_SM(SPEC) ? 256 : 128)
 template <int SPEC, int ILP>
 __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
     k_ensemble_cluster(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 double q[GF_MAX_DIM];
                 double lnew;
                 if (gf_ens_move<SPEC, ILP, true>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; }, lnp_s[h * T + wl], q, lnew)) {
-                    for (int d = 0; d < ndim; ++d) p[d] = q[d];
+                    _Pragma("unroll") for (int d = 0; d < GF_MAX_DIM; ++d)
+                        if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
                     lnp_s[h * T + wl] = lnew;
                     acc0 += h ? 0u : 1u;
                     acc1 += h ? 1u : 0u;
@@ -360,6 +361,7 @@ extern "C" int gf_ensemble_run(const gf_model* model, const gf_ensemble_config* 
     /* the per-point log-posterior specialisation gf_lnprob launches for this model (NPFREE -> GENERIC) */
     const int spec = gf_model_spec(d);
     if (spec == GF_SPEC_SM) return run_spec<GF_SPEC_SM, 1>(d, A, cfg, st);
+    if (spec == GF_SPEC_SM6) return run_spec<GF_SPEC_SM6, 1>(d, A, cfg, st);
     if (spec == GF_SPEC_FIXED) return run_spec<GF_SPEC_FIXED, GF_ENS_ILP_FIXED>(d, A, cfg, st);
     return run_spec<GF_SPEC_GENERIC, GF_ENS_ILP_GENERIC>(d, A, cfg, st);
 }

@@ -121,7 +121,8 @@ GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_
     const bool accept = gf_ens_move<SPEC, ILP, false>(
         m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew);
     if (accept) {
-        for (int d = 0; d < ndim; ++d) p[d] = q[d];
+        _Pragma("unroll") for (int d = 0; d < GF_MAX_DIM; ++d)
+                        if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
         A.lnp[c * A.nwalkers + k] = lnew;
     }
     return accept ? 1u : 0u;

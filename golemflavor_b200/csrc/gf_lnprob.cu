@@ -32,7 +32,7 @@ extern std::atomic<unsigned long long> g_gf_launches;
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 
 template <int KIND, int SPEC>
-__global__ void __launch_bounds__(GF_LP_THREADS, SPEC == GF_SPEC_SM ? 16 : GF_LP_MIN_BLOCKS)
+__global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(GF_LP_THREADS, SPEC == GF_SPEC_SM ? 16 : GF_LP
         if (status) status[i] = (uint8_t)st;
         return;
     }
-    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform) */
+    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform; for
+     * GF_SPEC_SM6 every k is a compile-time constant and repeated reads of a column are one load) */
     auto get = [&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); };
     if (KIND == GF_K_LNPRIOR) {
         lnp[i] = gf_point_lnprior(m, get);
@@ -111,6 +112,8 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
         k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else if (spec == GF_SPEC_SM)
         k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, (size_t)d.ndim * GF_LP_THREADS * sizeof(double), stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    else if (spec == GF_SPEC_SM6)
+        k_lnprob<KIND, GF_SPEC_SM6><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else
         k_lnprob<KIND, GF_SPEC_GENERIC><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     ++g_gf_launches;
@@ -247,6 +250,9 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else if (spec == GF_SPEC_SM)
             k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, (size_t)ndim * GF_LP_THREADS * sizeof(double), p.stream[s]>>>(
+                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        else if (spec == GF_SPEC_SM6)
+            k_lnprob<GF_K_LNPROB, GF_SPEC_SM6><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else
             k_lnprob<GF_K_LNPROB, GF_SPEC_GENERIC><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(

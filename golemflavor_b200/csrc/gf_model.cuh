@@ -65,6 +65,13 @@ struct gf_point {
  *                     registers the second interleaved bin chain needs.  Scan kernels only; the
  *                     log-posterior launcher serves such models with GF_SPEC_GENERIC. */
 #define GF_SPEC_NPFREE 3
+/*   GF_SPEC_SM6     : the SM-only model in the reference's own column layout (examples/inference.ipynb:
+ *                     columns 0-3 = s12^2, c13^4, s23^2, dcp, columns 4-5 = the two source angles, ndim = 6).
+ *                     Every theta read has a compile-time index, so the point lives in registers from the
+ *                     load to the likelihood: no shared-memory staging, no column-map lookups.  Other SM-only
+ *                     layouts run GF_SPEC_SM. */
+#define GF_SPEC_SM6 4
+#define GF_SPEC_IS_SM(SPEC) ((SPEC) == GF_SPEC_SM || (SPEC) == GF_SPEC_SM6)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -72,6 +79,14 @@ GF_HD int gf_model_spec(const gf_dev_model& m);
 /* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
 template <int SPEC = GF_SPEC_GENERIC, class Get>
 GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
+    if (SPEC == GF_SPEC_SM6) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        gfp_angles_to_fr(get(4), get(5), q.src);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
     if (SPEC != GF_SPEC_SM) {
@@ -173,7 +188,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
     unsigned st = 0u;
-    if (SPEC == GF_SPEC_SM || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
+    if (GF_SPEC_IS_SM(SPEC) || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
         double X[9];
         gfp_pmns_abs2_coords(q.sm[0], q.sm[1], q.sm[2], q.sm[3], X);
         double f[3];
@@ -182,7 +197,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         fr[0] = f[0] * inv;
         fr[1] = f[1] * inv;
         fr[2] = f[2] * inv;
-    } else if (SPEC != GF_SPEC_SM) {
+    } else if (!GF_SPEC_IS_SM(SPEC)) {
         const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
         const gfp_cols12 u = gfp_cols_from_trig(t);
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
@@ -231,7 +246,11 @@ GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) { return !m.no_bsm && !
 /* which specialisation the host launches for a model (kernels without a GF_SPEC_NPFREE instance map it
  * to GF_SPEC_GENERIC) */
 GF_HD int gf_model_spec(const gf_dev_model& m) {
-    if (m.no_bsm) return GF_SPEC_SM;
+    if (m.no_bsm) {
+        const bool canon = m.ndim == 6 && m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3 &&
+                           m.col_src[0] == 4 && m.col_src[1] == 5 && m.col_x < 0 && m.col_src3[0] < 0;
+        return canon ? GF_SPEC_SM6 : GF_SPEC_SM;
+    }
     if (!gf_model_has_fixed_source(m)) return GF_SPEC_GENERIC;
     return m.np_free ? GF_SPEC_NPFREE : GF_SPEC_FIXED;
 }
@@ -239,7 +258,7 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.
  * Branch-free per dimension: uniform dimensions carry inv_sigma = 0 (their z vanishes) and the
  * normalisers of all Gaussian dimensions are pre-summed on the host (m.lognorm_total). */
-template <class Get>
+template <int NDIM = 0, class Get>
 GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
     double acc = 0.0;
     bool inside = true;
@@ -247,8 +266,8 @@ GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
      * prior tables are constant-bank operands of the compares and the FMA instead of indexed constant
      * loads -- the rolled loop was 21 % of the instructions of the SM-only kernel */
 #pragma unroll
-    for (int k = 0; k < GF_MAX_DIM; ++k) {
-        if (k >= m.ndim) break;
+    for (int k = 0; k < (NDIM > 0 ? NDIM : GF_MAX_DIM); ++k) {
+        if (NDIM == 0 && k >= m.ndim) break;
         const double v = get(k);
         inside = inside && (v >= m.lo[k]) && (v <= m.hi[k]);
         const double z = (v - m.mu[k]) * m.inv_sigma[k];
@@ -269,7 +288,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
-    const double lp = gf_point_lnprior(m, get);
+    const double lp = gf_point_lnprior<SPEC == GF_SPEC_SM6 ? 6 : 0>(m, get);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
         fr[0] = fr[1] = fr[2] = NAN;
         st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;

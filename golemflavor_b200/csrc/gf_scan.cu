@@ -127,7 +127,8 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     const bool use_smem = smem <= kSmemHistLimit;
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
-    const int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
+    int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
+    if (spec == GF_SPEC_SM6) spec = GF_SPEC_SM; /* the scans keep one SM-only instance */
     auto kern_s = spec == GF_SPEC_FIXED    ? k_hist<SCAN, true, GF_SPEC_FIXED>
                   : spec == GF_SPEC_SM     ? k_hist<SCAN, true, GF_SPEC_SM>
                   : spec == GF_SPEC_NPFREE ? k_hist<SCAN, true, GF_SPEC_NPFREE>

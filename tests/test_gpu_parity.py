@@ -229,6 +229,40 @@ def test_golden_multi_gaussian(torch, golden):
 
 
 # ------------------------------------------------------------------ oracle on seeded inputs
+
+
+def test_sm_only_column_layouts_agree(torch, golden):
+    """The SM-only log-posterior has a register-resident specialisation for the reference's own column
+    layout (4 mixing coordinates, then the 2 source angles) and a column-map path (theta staged in shared
+    memory) for every other layout: the same model with its columns permuted must give the same values,
+    in both theta layouts (row-major and SoA), and both must match the oracle."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    from golemflavor_b200.param import ParamSet
+    perm = [4, 0, 1, 5, 2, 3]      # interleaved; the order within a tag is what identifies a parameter (param.py:185-199)
+    pset_p = ParamSet([pset[k] for k in perm])
+    fn, fn_p = llh.LnProb(args, asimov, pset), llh.LnProb(args, asimov, pset_p)
+    rng = np.random.default_rng(12)
+    theta = models.draw_in_ranges(pset, 5000, rng)
+    theta[:50, 0] = rng.uniform(-0.2, 1.2, 50)            # some points outside the prior box
+    a, fa, _ = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    b, fb, _ = (x.cpu().numpy() for x in fn_p.evaluate(theta[:, perm], want_fr=True, want_status=True))
+    fin = np.isfinite(a)
+    assert np.array_equal(fin, np.isfinite(b)) and 4000 < fin.sum() < 5000
+    assert np.allclose(a[fin], b[fin], rtol=1e-13, atol=0) and np.array_equal(fa[fin], fb[fin])
+    t = torch.as_tensor(theta).cuda()
+    soa = t.t().contiguous().t()                           # same values, column-major storage
+    assert np.array_equal(fn(soa).cpu().numpy()[fin], a[fin])
+    tp = torch.as_tensor(np.ascontiguousarray(theta[:, perm])).cuda()
+    assert np.array_equal(fn_p(tp.t().contiguous().t()).cpu().numpy()[fin], b[fin])
+    lo, hi = np.array(pset.ranges).T
+    kind = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in pset]
+    ref_fr = go.batch_u_to_fr(np.array(go.batch_angles_to_fr(theta[:, 4:6])).astype(float), go.batch_angles_to_u(theta[:, :4])).astype(float)
+    ref = go.batch_lnprior(theta, lo, hi, kind, list(pset.nominal_values), [p.std or 1.0 for p in pset]) + \
+        go.batch_multi_gaussian(ref_fr, go.angles_to_fr(g['asimov_angles']), 0.02)
+    assert np.max(np.abs(a[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+
+
 @pytest.mark.parametrize('texture', ['OET', 'OUT', 'OEU'])
 @pytest.mark.parametrize('dim', [3, 6, 8])
 def test_bsm_lnprob_against_oracle(torch, golden, texture, dim):
