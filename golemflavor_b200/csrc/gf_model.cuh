@@ -72,6 +72,12 @@ struct gf_point {
  *                     layouts run GF_SPEC_SM. */
 #define GF_SPEC_SM6 4
 #define GF_SPEC_IS_SM(SPEC) ((SPEC) == GF_SPEC_SM || (SPEC) == GF_SPEC_SM6)
+/*   GF_SPEC_FIXED7  : GF_SPEC_FIXED in the column layout of scripts/fr.py (columns 0-3 = the four mixing
+ *                     coordinates, 4-5 = the mass-squared differences, 6 = logLam, ndim = 7): compile-time
+ *                     theta indices as in GF_SPEC_SM6.  Log-posterior and sampler kernels; the scans run it
+ *                     as GF_SPEC_FIXED. */
+#define GF_SPEC_FIXED7 5
+#define GF_SPEC_IS_FIXED(SPEC) ((SPEC) == GF_SPEC_FIXED || (SPEC) == GF_SPEC_FIXED7)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -87,6 +93,16 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         gfp_angles_to_fr(get(4), get(5), q.src);
         return;
     }
+    if (SPEC == GF_SPEC_FIXED7) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.mass[0] = get(4);
+        q.mass[1] = get(5);
+        q.loglam = get(6);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
     if (SPEC != GF_SPEC_SM) {
@@ -98,7 +114,7 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
     if (SPEC != GF_SPEC_SM) q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
-    if (SPEC == GF_SPEC_FIXED || SPEC == GF_SPEC_NPFREE) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
+    if (GF_SPEC_IS_FIXED(SPEC) || SPEC == GF_SPEC_NPFREE) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
     } else if (m.col_src3[0] >= 0) {
@@ -209,7 +225,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
 #else
         const double lam = pow(10.0, q.loglam);
 #endif
-        if (SPEC == GF_SPEC_FIXED) {
+        if (GF_SPEC_IS_FIXED(SPEC)) {
             gfp_herm3 T = m.T;
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
             st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
@@ -252,7 +268,10 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
         return canon ? GF_SPEC_SM6 : GF_SPEC_SM;
     }
     if (!gf_model_has_fixed_source(m)) return GF_SPEC_GENERIC;
-    return m.np_free ? GF_SPEC_NPFREE : GF_SPEC_FIXED;
+    if (m.np_free) return GF_SPEC_NPFREE;
+    const bool canon = m.ndim == 7 && m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3 &&
+                       m.col_mass[0] == 4 && m.col_mass[1] == 5 && m.col_scale == 6;
+    return canon ? GF_SPEC_FIXED7 : GF_SPEC_FIXED;
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.
@@ -288,7 +307,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
-    const double lp = gf_point_lnprior<SPEC == GF_SPEC_SM6 ? 6 : 0>(m, get);
+    const double lp = gf_point_lnprior<SPEC == GF_SPEC_SM6 ? 6 : SPEC == GF_SPEC_FIXED7 ? 7 : 0>(m, get);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
         fr[0] = fr[1] = fr[2] = NAN;
         st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;

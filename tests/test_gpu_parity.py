@@ -263,6 +263,24 @@ def test_sm_only_column_layouts_agree(torch, golden):
     assert np.max(np.abs(a[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
 
 
+def test_bsm_fixed_texture_column_layouts_agree(torch, golden):
+    """Same for the fixed-texture BSM model: the scripts/fr.py column layout (4 mixing coordinates, 2 mass
+    splittings, logLam) runs with compile-time theta indices, any other layout through the column map --
+    identical compositions, log-posteriors equal up to the summation order of the prior terms."""
+    from golemflavor_b200.param import ParamSet
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OUT)
+    perm = [6, 0, 4, 1, 2, 5, 3]       # logLam first, masses interleaved; order within a tag preserved
+    fn, fn_p = llh.LnProb(args, asimov, pset), llh.LnProb(args, asimov, ParamSet([pset[k] for k in perm]))
+    rng = np.random.default_rng(13)
+    theta = models.draw_in_ranges(pset, 20000, rng)
+    a, fa, sa = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    b, fb, sb = (x.cpu().numpy() for x in fn_p.evaluate(theta[:, perm], want_fr=True, want_status=True))
+    assert np.all(np.isfinite(a)) and np.array_equal(fa, fb) and np.array_equal(sa, sb)
+    assert np.allclose(a, b, rtol=1e-13, atol=0)
+    assert (sa & _lib.ST_REFINED).any()                  # the near-degenerate fallback is exercised on both paths
+
+
 @pytest.mark.parametrize('texture', ['OET', 'OUT', 'OEU'])
 @pytest.mark.parametrize('dim', [3, 6, 8])
 def test_bsm_lnprob_against_oracle(torch, golden, texture, dim):
