@@ -245,7 +245,9 @@ class DeviceEnsembleSampler(object):
             lnp = None if lnprob0 is None else _lib.to_device(lnprob0, torch).reshape(self.nchains, self.k).clone()
         if lnp is None:
             lnp = self.lnprob.evaluate(pos.reshape(-1, self.dim)).reshape(self.nchains, self.k)
-        if bool(torch.isnan(lnp).any()):
+        # emcee raises on a NaN log-probability; only freshly supplied positions can carry one (the move
+        # rejects NaN proposals), and skipping the check on continuation keeps run_mcmc asynchronous
+        if pos0 is not None and bool(torch.isnan(lnp).any()):
             raise ValueError('lnprob returned NaN.')
         nstore = int(N) // int(thin) if store else 0
         chain = torch.empty((self.nchains, self.k, nstore, self.dim), dtype=torch.float64, device='cuda') if nstore else None

@@ -57,6 +57,9 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
     src = np.asarray(source_ratio, dtype=np.float64)
     inj = np.asarray(injected_ratio, dtype=np.float64)
     rng = np.random.RandomState(seed)
+    # one CUDA stream per dimension: the launches of different dimensions (different models, hence different
+    # kernel launches) are latency-bound single-warp clusters and run side by side on the SMs
+    pending = []
     for dim in sorted({d for d, _ in mine}):
         idx = [start + i for i, (d, _) in enumerate(mine) if d == dim]
         scales = np.array([grid[i][1] for i in idx])
@@ -70,13 +73,18 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
         p0 = np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)])
         np.random.set_state(state)
         p0[:, :, ndim - 1] = scales[:, None]                      # frozen column: identical in all walkers
-        sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, nchains=nchains, seed=seed + 1000 * dim, nfree=ndim - 1,
-                                        chain0=idx[0])
-        sampler.run_mcmc(p0, burnin, store=False)
-        sampler.reset()
-        pos, lnp, _ = sampler.run_mcmc(None, nsteps, store=False, return_tensor=True)
-        # summaries from the final ensemble + the acceptance counters (no chain leaves the device)
-        _, fr, _ = fn.evaluate(pos.reshape(-1, ndim), want_fr=True, want_status=True)
+        stream = torch.cuda.Stream()
+        with torch.cuda.stream(stream):
+            sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, nchains=nchains, seed=seed + 1000 * dim, nfree=ndim - 1,
+                                            chain0=idx[0])
+            sampler.run_mcmc(p0, burnin, store=False, return_tensor=True)
+            sampler.reset()
+            pos, lnp, _ = sampler.run_mcmc(None, nsteps, store=False, return_tensor=True)
+            # summaries from the final ensemble + the acceptance counters (no chain leaves the device)
+            _, fr, _ = fn.evaluate(pos.reshape(-1, ndim), want_fr=True, want_status=True)
+        pending.append((stream, dim, idx, scales, sampler, lnp, fr, nchains))
+    for stream, dim, idx, scales, sampler, lnp, fr, nchains in pending:
+        stream.synchronize()
         fr = fr.reshape(nchains, nwalkers, 3)
         acc = torch.as_tensor(np.atleast_2d(sampler.acceptance_fraction), device='cuda').reshape(nchains, nwalkers)
         ii = torch.as_tensor(idx, device='cuda')
