@@ -159,6 +159,12 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
 #endif
     /* software pipeline: the draws of the NEXT half-step (Philox, stretch factor, both logarithms -- nothing
      * that depends on a walker position) are computed between the arrive and the wait of the cluster barrier */
+    /* chain output of this thread's two walkers (emcee layout [walker][slot][dim]) */
+    int64_t until_store = A.thin, stored = 0;
+    double* out0 = A.chain ? A.chain + (c * A.nwalkers + w) * nstore * ndim : nullptr;
+    double* out1 = A.chain ? A.chain + (c * A.nwalkers + half + w) * nstore * ndim : nullptr;
+    double* lout0 = A.lnp_chain ? A.lnp_chain + (c * A.nwalkers + w) * nstore : nullptr;
+    double* lout1 = A.lnp_chain ? A.lnp_chain + (c * A.nwalkers + half + w) * nstore : nullptr;
     gf_ens_draw dr;
     if (active) {
         dr = gf_ens_draws(A, gid0, A.step0, half);
@@ -190,19 +196,32 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 dr = gf_ens_draws(A, gid0 + (uint64_t)((1 - h) * half), A.step0 + s + h, half);
                 gf_ens_finish_draw(A, dr);
                 GF_TICK(t_draw)
+                /* the step is complete for this thread's two walkers once its own second-half update is
+                 * done (only their owner writes them): store them in the shadow of the barrier as well */
+                if (h == 1 && --until_store == 0) {
+                    until_store = A.thin;
+                    if (stored < nstore) { /* running output pointers: no 64-bit index arithmetic per store */
+                        if (A.chain) {
+#pragma unroll
+                            for (int d = 0; d < GF_MAX_DIM; ++d) {
+                                if (d < ndim) {
+                                    out0[d] = pos_s[wl * ndim + d];
+                                    out1[d] = pos_s[(T + wl) * ndim + d];
+                                }
+                            }
+                            out0 += ndim;
+                            out1 += ndim;
+                        }
+                        if (A.lnp_chain) {
+                            *lout0++ = lnp_s[wl];
+                            *lout1++ = lnp_s[T + wl];
+                        }
+                        ++stored;
+                    }
+                }
             }
             cluster.barrier_wait();
             GF_TICK(t_sync)
-        }
-        if (active && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) {
-            const int64_t slot = (s + 1) / A.thin - 1;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const int64_t k = c * A.nwalkers + h * half + w;
-                if (A.chain)
-                    for (int d = 0; d < ndim; ++d) A.chain[(k * nstore + slot) * ndim + d] = pos_s[(h * T + wl) * ndim + d];
-                if (A.lnp_chain) A.lnp_chain[k * nstore + slot] = lnp_s[h * T + wl];
-            }
         }
     }
 #ifdef GF_ENS_PROFILE
