@@ -270,6 +270,15 @@ def run_gpu(opts):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * e2e_steps / e2e_s
     assert np.array_equal(out_np, out.cpu().numpy()), 'host pipeline and device path disagree'
+    # context for e2e: the plain pinned-host -> device copy rate of the same theta buffer (the link ceiling)
+    link = 0.0
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        theta.copy_(theta_host, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link = max(link, theta_host.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
     finite_frac = float(np.isfinite(out_np).mean())
 
     # -- secondary: sharded Monte-Carlo scan with the histogram all-reduce (config 4)
@@ -388,7 +397,9 @@ def run_gpu(opts):
                                  'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
             'cpu_baseline': base,
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': n * fn.ndim * 8, 'd2h_bytes_per_step': n * 8,
-                    'steps': e2e_steps, 'api': 'golemflavor_b200.llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)'},
+                    'steps': e2e_steps, 'api': 'golemflavor_b200.llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)',
+                    'h2d_gbs': e2e_value / world * fn.ndim * 8 / 1e9, 'h2d_link_gbs': link,
+                    'note': 'bound by the host link: h2d_gbs is the input rate the pipeline sustains per GPU, h2d_link_gbs a plain pinned copy of the same buffer'},
             'gpu_launches': int(launches),
             'clocks': clock_info,
             'scan': scan_info,
