@@ -281,6 +281,45 @@ def test_bsm_fixed_texture_column_layouts_agree(torch, golden):
     assert (sa & _lib.ST_REFINED).any()                  # the near-degenerate fallback is exercised on both paths
 
 
+def test_production_paramset_of_fr_script_with_golemfit_nuisances(torch, golden):
+    """scripts/fr.py:30-90 fits 12 parameters: six SM_ANGLES, five NUISANCE-tagged GolemFit normalisations
+    and logLam.  The nuisances only enter the (proprietary) GolemFit likelihood; with the Gaussian stand-in
+    they contribute their priors and nothing else: the 12-column model must equal the oracle's prior over all
+    twelve columns plus the likelihood of the seven physical ones."""
+    from golemflavor_b200.enums import ParamTag, PriorsCateg
+    from golemflavor_b200.param import Param, ParamSet
+    g = golden('ref_llh.npz')
+    args, asimov, p7 = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
+    lg, tag = PriorsCateg.LIMITEDGAUSS, ParamTag.NUISANCE
+    nuis = [Param(name='convNorm', value=1., seed=[0.5, 2.], ranges=[0.1, 10.], std=0.4, prior=lg, tag=tag),
+            Param(name='promptNorm', value=0., seed=[0., 6.], ranges=[0., 20.], std=2.4, prior=lg, tag=tag),
+            Param(name='muonNorm', value=1., seed=[0.1, 2.], ranges=[0., 10.], std=0.1, tag=tag),
+            Param(name='astroNorm', value=6.9, seed=[0., 5.], ranges=[0., 20.], std=1.5, tag=tag),
+            Param(name='astroDeltaGamma', value=2.5, seed=[2.4, 3.], ranges=[-5., 5.], std=0.1, tag=tag)]
+    p12 = ParamSet(list(p7)[:6] + nuis + [p7[6]])
+    fn = llh.LnProb(args, asimov, p12)
+    rng = np.random.default_rng(21)
+    theta = models.draw_in_ranges(p12, 4000, rng, seeds=True)
+    theta[:, 11] = rng.uniform(*model.SCALE_BOUNDARIES[6], 4000)
+    theta[:40, 8] = rng.uniform(-1, 11, 40)                 # some nuisance values outside their box
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    phys = theta[:, [0, 1, 2, 3, 4, 5, 11]]
+    ref_fr = truth.eigh_flux_averaged_fr(phys[:, :4], phys[:, 4:6], model.TEXTURE_ANGLES['OET'], phys[:, 6], 6,
+                                         models.BINNING, args.source_ratio)
+    lo, hi = np.array(p12.ranges).T
+    kind = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in p12]
+    ref = go.batch_lnprior(theta, lo, hi, kind, list(p12.nominal_values), [p.std or 1.0 for p in p12]) + \
+        go.batch_multi_gaussian(ref_fr, go.angles_to_fr(g['asimov_angles']), 0.02)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lnp), fin) and 3900 < fin.sum() < 4000
+    assert np.abs(frs[fin] - ref_fr[fin]).max() < FR_TOL
+    assert np.max(np.abs(lnp[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+    # the nuisance columns do not touch the composition: same values through the 7-column model
+    f7 = llh.LnProb(args, asimov, p7)
+    _, fr7, _ = (x.cpu().numpy() for x in f7.evaluate(phys, want_fr=True, want_status=True))
+    assert np.array_equal(fr7[fin], frs[fin])
+
+
 @pytest.mark.parametrize('texture', ['OET', 'OUT', 'OEU'])
 @pytest.mark.parametrize('dim', [3, 6, 8])
 def test_bsm_lnprob_against_oracle(torch, golden, texture, dim):
