@@ -383,5 +383,6 @@ extern "C" int gf_ensemble_run(const gf_model* model, const gf_ensemble_config* 
     if (spec == GF_SPEC_SM6) return run_spec<GF_SPEC_SM6, 1>(d, A, cfg, st);
     if (spec == GF_SPEC_FIXED) return run_spec<GF_SPEC_FIXED, GF_ENS_ILP_FIXED>(d, A, cfg, st);
     if (spec == GF_SPEC_FIXED7) return run_spec<GF_SPEC_FIXED7, GF_ENS_ILP_FIXED>(d, A, cfg, st);
+    if (spec == GF_SPEC_FIXED12) return run_spec<GF_SPEC_FIXED12, GF_ENS_ILP_FIXED>(d, A, cfg, st);
     return run_spec<GF_SPEC_GENERIC, GF_ENS_ILP_GENERIC>(d, A, cfg, st);
 }

@@ -112,6 +112,8 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
         k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else if (spec == GF_SPEC_FIXED7)
         k_lnprob<KIND, GF_SPEC_FIXED7><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    else if (spec == GF_SPEC_FIXED12)
+        k_lnprob<KIND, GF_SPEC_FIXED12><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else if (spec == GF_SPEC_SM)
         k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, (size_t)d.ndim * GF_LP_THREADS * sizeof(double), stream>>>(d, th, n, d_lnp, d_fr, d_status);
     else if (spec == GF_SPEC_SM6)
@@ -252,6 +254,9 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else if (spec == GF_SPEC_FIXED7)
             k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED7><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
+                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        else if (spec == GF_SPEC_FIXED12)
+            k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED12><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
                 d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
         else if (spec == GF_SPEC_SM)
             k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, (size_t)ndim * GF_LP_THREADS * sizeof(double), p.stream[s]>>>(

@@ -77,7 +77,12 @@ struct gf_point {
  *                     theta indices as in GF_SPEC_SM6.  Log-posterior and sampler kernels; the scans run it
  *                     as GF_SPEC_FIXED. */
 #define GF_SPEC_FIXED7 5
-#define GF_SPEC_IS_FIXED(SPEC) ((SPEC) == GF_SPEC_FIXED || (SPEC) == GF_SPEC_FIXED7)
+/*   GF_SPEC_FIXED12 : the same with the five GolemFit nuisance columns of scripts/fr.py:54-60 between the
+ *                     masses and logLam (columns 6-10 carry priors only, logLam is column 11, ndim = 12) --
+ *                     the reference's production parameter set. */
+#define GF_SPEC_FIXED12 6
+#define GF_SPEC_IS_FIXED(SPEC) ((SPEC) == GF_SPEC_FIXED || (SPEC) == GF_SPEC_FIXED7 || (SPEC) == GF_SPEC_FIXED12)
+#define GF_SPEC_STATIC_NDIM(SPEC) ((SPEC) == GF_SPEC_SM6 ? 6 : (SPEC) == GF_SPEC_FIXED7 ? 7 : (SPEC) == GF_SPEC_FIXED12 ? 12 : 0)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -93,14 +98,14 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         gfp_angles_to_fr(get(4), get(5), q.src);
         return;
     }
-    if (SPEC == GF_SPEC_FIXED7) {
+    if (SPEC == GF_SPEC_FIXED7 || SPEC == GF_SPEC_FIXED12) {
         q.sm[0] = get(0);
         q.sm[1] = get(1);
         q.sm[2] = get(2);
         q.sm[3] = get(3);
         q.mass[0] = get(4);
         q.mass[1] = get(5);
-        q.loglam = get(6);
+        q.loglam = get(SPEC == GF_SPEC_FIXED12 ? 11 : 6);
         return;
     }
 #pragma unroll
@@ -269,9 +274,10 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
     }
     if (!gf_model_has_fixed_source(m)) return GF_SPEC_GENERIC;
     if (m.np_free) return GF_SPEC_NPFREE;
-    const bool canon = m.ndim == 7 && m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3 &&
-                       m.col_mass[0] == 4 && m.col_mass[1] == 5 && m.col_scale == 6;
-    return canon ? GF_SPEC_FIXED7 : GF_SPEC_FIXED;
+    const bool head = m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3 && m.col_mass[0] == 4 && m.col_mass[1] == 5;
+    if (head && m.ndim == 7 && m.col_scale == 6) return GF_SPEC_FIXED7;
+    if (head && m.ndim == 12 && m.col_scale == 11) return GF_SPEC_FIXED12;
+    return GF_SPEC_FIXED;
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.
@@ -307,7 +313,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
-    const double lp = gf_point_lnprior<SPEC == GF_SPEC_SM6 ? 6 : SPEC == GF_SPEC_FIXED7 ? 7 : 0>(m, get);
+    const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC)>(m, get);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
         fr[0] = fr[1] = fr[2] = NAN;
         st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;

@@ -129,7 +129,7 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     if (int rc = gf_sm_count(&sms)) return rc;
     int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
     if (spec == GF_SPEC_SM6) spec = GF_SPEC_SM; /* the scans keep one SM-only and one fixed-texture instance */
-    if (spec == GF_SPEC_FIXED7) spec = GF_SPEC_FIXED;
+    if (spec == GF_SPEC_FIXED7 || spec == GF_SPEC_FIXED12) spec = GF_SPEC_FIXED;
     auto kern_s = spec == GF_SPEC_FIXED    ? k_hist<SCAN, true, GF_SPEC_FIXED>
                   : spec == GF_SPEC_SM     ? k_hist<SCAN, true, GF_SPEC_SM>
                   : spec == GF_SPEC_NPFREE ? k_hist<SCAN, true, GF_SPEC_NPFREE>

@@ -318,6 +318,20 @@ def test_production_paramset_of_fr_script_with_golemfit_nuisances(torch, golden)
     f7 = llh.LnProb(args, asimov, p7)
     _, fr7, _ = (x.cpu().numpy() for x in f7.evaluate(phys, want_fr=True, want_status=True))
     assert np.array_equal(fr7[fin], frs[fin])
+    # ... and through the column-map path (this layout has its own compile-time specialisation): logLam first
+    perm = [11] + list(range(11))
+    fp = llh.LnProb(args, asimov, ParamSet([p12[k] for k in perm]))
+    lp, frp, _ = (x.cpu().numpy() for x in fp.evaluate(theta[:, perm], want_fr=True, want_status=True))
+    assert np.array_equal(frp[fin], frs[fin]) and np.allclose(lp[fin], lnp[fin], rtol=1e-13, atol=0)
+    # the device sampler on the 12-parameter model: every launch shape gives the same chain
+    np.random.seed(5)
+    p0 = mcmc.flat_seed(p12, 64)
+    ref = mcmc.DeviceEnsembleSampler(64, 12, fn, seed=2, mode=1)
+    ref.run_mcmc(p0, 8)
+    for mode in (0, 2):
+        s = mcmc.DeviceEnsembleSampler(64, 12, fn, seed=2, mode=mode)
+        s.run_mcmc(p0, 8)
+        assert np.array_equal(s.chain, ref.chain)
 
 
 @pytest.mark.parametrize('texture', ['OET', 'OUT', 'OEU'])
