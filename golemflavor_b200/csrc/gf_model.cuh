@@ -82,7 +82,18 @@ struct gf_point {
  *                     the reference's production parameter set. */
 #define GF_SPEC_FIXED12 6
 #define GF_SPEC_IS_FIXED(SPEC) ((SPEC) == GF_SPEC_FIXED || (SPEC) == GF_SPEC_FIXED7 || (SPEC) == GF_SPEC_FIXED12)
-#define GF_SPEC_STATIC_NDIM(SPEC) ((SPEC) == GF_SPEC_SM6 ? 6 : (SPEC) == GF_SPEC_FIXED7 ? 7 : (SPEC) == GF_SPEC_FIXED12 ? 12 : 0)
+/*   GF_SPEC_SM4, GF_SPEC_NPFREE11 : scan kernels only -- the unitary scan (columns 0-3 = the mixing
+ *                     coordinates, fixed source, ndim = 4) and the anarchic scan (0-3 mixing, 4-5 masses,
+ *                     6-9 NP mixing, 10 logLam, fixed source, ndim = 11) in the layouts scan.scan_paramset
+ *                     produces; the texture scan is GF_SPEC_FIXED7.  The drawn sample stays in registers. */
+#define GF_SPEC_SM4 7
+#define GF_SPEC_NPFREE11 8
+#undef GF_SPEC_IS_SM
+#define GF_SPEC_IS_SM(SPEC) ((SPEC) == GF_SPEC_SM || (SPEC) == GF_SPEC_SM6 || (SPEC) == GF_SPEC_SM4)
+#define GF_SPEC_IS_NPFREE(SPEC) ((SPEC) == GF_SPEC_NPFREE || (SPEC) == GF_SPEC_NPFREE11)
+#define GF_SPEC_STATIC_NDIM(SPEC)                                                                                  \
+    ((SPEC) == GF_SPEC_SM6 ? 6 : (SPEC) == GF_SPEC_FIXED7 ? 7 : (SPEC) == GF_SPEC_FIXED12 ? 12 : (SPEC) == GF_SPEC_SM4 ? 4 : \
+     (SPEC) == GF_SPEC_NPFREE11 ? 11 : 0)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -96,6 +107,30 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         q.sm[2] = get(2);
         q.sm[3] = get(3);
         gfp_angles_to_fr(get(4), get(5), q.src);
+        return;
+    }
+    if (SPEC == GF_SPEC_SM4) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.src[0] = m.fixed_src[0];
+        q.src[1] = m.fixed_src[1];
+        q.src[2] = m.fixed_src[2];
+        return;
+    }
+    if (SPEC == GF_SPEC_NPFREE11) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.mass[0] = get(4);
+        q.mass[1] = get(5);
+        q.np[0] = get(6);
+        q.np[1] = get(7);
+        q.np[2] = get(8);
+        q.np[3] = get(9);
+        q.loglam = get(10);
         return;
     }
     if (SPEC == GF_SPEC_FIXED7 || SPEC == GF_SPEC_FIXED12) {
@@ -114,12 +149,12 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) q.mass[k] = m.col_mass[k] >= 0 ? get(m.col_mass[k]) : m.fixed_mass[k];
     }
-    if ((SPEC == GF_SPEC_GENERIC && m.np_free) || SPEC == GF_SPEC_NPFREE) {
+    if ((SPEC == GF_SPEC_GENERIC && m.np_free) || GF_SPEC_IS_NPFREE(SPEC)) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
     if (SPEC != GF_SPEC_SM) q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
-    if (GF_SPEC_IS_FIXED(SPEC) || SPEC == GF_SPEC_NPFREE) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
+    if (GF_SPEC_IS_FIXED(SPEC) || GF_SPEC_IS_NPFREE(SPEC)) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
     if (m.col_src[0] >= 0) {
         gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
     } else if (m.col_src3[0] >= 0) {
@@ -236,15 +271,15 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
             st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
         } else {
             gfp_herm3 T;
-            if (SPEC == GF_SPEC_NPFREE || m.np_free) {
+            if (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) {
                 const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
                 T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
             } else {
                 T = m.T;
             }
             const gfp_pencil_T pt = gfp_make_pencil_T(T);
-            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, (SPEC == GF_SPEC_NPFREE || m.np_free) ? gfp_adj_tf(pt.te, T) : m.adjT);
-            if (SPEC == GF_SPEC_NPFREE) {
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) ? gfp_adj_tf(pt.te, T) : m.adjT);
+            if (GF_SPEC_IS_NPFREE(SPEC)) {
                 st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
             } else {
                 const double S = q.src[0] + q.src[1] + q.src[2];
@@ -278,6 +313,21 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
     if (head && m.ndim == 7 && m.col_scale == 6) return GF_SPEC_FIXED7;
     if (head && m.ndim == 12 && m.col_scale == 11) return GF_SPEC_FIXED12;
     return GF_SPEC_FIXED;
+}
+
+/* which specialisation the scan kernels launch: their own compile-time layouts where the model has one */
+GF_HD int gf_model_scan_spec(const gf_dev_model& m) {
+    const int spec = gf_model_spec(m);
+    const bool sm03 = m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3;
+    if (spec == GF_SPEC_SM6) return GF_SPEC_SM;
+    if (spec == GF_SPEC_SM) return (sm03 && m.ndim == 4 && gf_model_has_fixed_source(m)) ? GF_SPEC_SM4 : GF_SPEC_SM;
+    if (spec == GF_SPEC_FIXED12) return GF_SPEC_FIXED;
+    if (spec == GF_SPEC_NPFREE) {
+        const bool canon = sm03 && m.ndim == 11 && m.col_mass[0] == 4 && m.col_mass[1] == 5 && m.col_np[0] == 6 && m.col_np[1] == 7 &&
+                           m.col_np[2] == 8 && m.col_np[3] == 9 && m.col_scale == 10;
+        return canon ? GF_SPEC_NPFREE11 : GF_SPEC_NPFREE;
+    }
+    return spec; /* GENERIC, FIXED, FIXED7 */
 }
 
 /* llh.lnprior (llh.py:74-90): -inf outside the box, sum of (truncated) Gaussian log-pdfs inside.

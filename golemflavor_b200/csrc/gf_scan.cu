@@ -35,7 +35,7 @@ extern std::atomic<unsigned long long> g_gf_launches;
 
 /* Source of compositions: drawn samples (SCAN) or a given array (GIVEN). */
 template <bool SCAN, bool SMEM_HIST, int SPEC>
-__global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_SCAN_MIN_BLOCKS) /* BSM: <= 128 registers, two 256-thread blocks (2 x 70 KB histograms) per SM; SM-only: three */
+__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SPEC_IS_SM(SPEC) ? 3 : GF_SCAN_MIN_BLOCKS) /* BSM: <= 128 registers, two 256-thread blocks (2 x 70 KB histograms) per SM; SM-only: three */
     k_hist(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
            const double* __restrict__ fr_in, const int nb1, const double step, unsigned long long* __restrict__ hist,
            unsigned long long* __restrict__ accepted) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(GF_SCAN_THREADS, SPEC == GF_SPEC_SM ? 3 : GF_S
         double fr[3];
         if (SCAN) {
             double theta[GF_MAX_DIM];
-            gf_draw_theta<SPEC == GF_SPEC_SM>(m, seed, first_index + j, theta);
+            gf_draw_theta<GF_SPEC_IS_SM(SPEC) || (GF_SPEC_STATIC_NDIM(SPEC) > 0), GF_SPEC_STATIC_NDIM(SPEC)>(m, seed, first_index + j, theta);
             gf_point q;
             gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
             gf_point_fr<SPEC, GF_SCAN_ILP_FOR(SPEC)>(m, q, fr);
@@ -127,17 +127,18 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     const bool use_smem = smem <= kSmemHistLimit;
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
-    int spec = SCAN ? gf_model_spec(d) : GF_SPEC_GENERIC;
-    if (spec == GF_SPEC_SM6) spec = GF_SPEC_SM; /* the scans keep one SM-only and one fixed-texture instance */
-    if (spec == GF_SPEC_FIXED7 || spec == GF_SPEC_FIXED12) spec = GF_SPEC_FIXED;
-    auto kern_s = spec == GF_SPEC_FIXED    ? k_hist<SCAN, true, GF_SPEC_FIXED>
-                  : spec == GF_SPEC_SM     ? k_hist<SCAN, true, GF_SPEC_SM>
-                  : spec == GF_SPEC_NPFREE ? k_hist<SCAN, true, GF_SPEC_NPFREE>
-                                           : k_hist<SCAN, true, GF_SPEC_GENERIC>;
-    auto kern_g = spec == GF_SPEC_FIXED    ? k_hist<SCAN, false, GF_SPEC_FIXED>
-                  : spec == GF_SPEC_SM     ? k_hist<SCAN, false, GF_SPEC_SM>
-                  : spec == GF_SPEC_NPFREE ? k_hist<SCAN, false, GF_SPEC_NPFREE>
-                                           : k_hist<SCAN, false, GF_SPEC_GENERIC>;
+    const int spec = SCAN ? gf_model_scan_spec(d) : GF_SPEC_GENERIC;
+#define GF_HIST_KERNEL(SMEM)                                                                  \
+    (spec == GF_SPEC_FIXED      ? k_hist<SCAN, SMEM, GF_SPEC_FIXED>                           \
+     : spec == GF_SPEC_FIXED7   ? k_hist<SCAN, SMEM, GF_SPEC_FIXED7>                          \
+     : spec == GF_SPEC_SM       ? k_hist<SCAN, SMEM, GF_SPEC_SM>                              \
+     : spec == GF_SPEC_SM4      ? k_hist<SCAN, SMEM, GF_SPEC_SM4>                             \
+     : spec == GF_SPEC_NPFREE   ? k_hist<SCAN, SMEM, GF_SPEC_NPFREE>                          \
+     : spec == GF_SPEC_NPFREE11 ? k_hist<SCAN, SMEM, GF_SPEC_NPFREE11>                        \
+                                : k_hist<SCAN, SMEM, GF_SPEC_GENERIC>)
+    auto kern_s = GF_HIST_KERNEL(true);
+    auto kern_g = GF_HIST_KERNEL(false);
+#undef GF_HIST_KERNEL
     int per_sm = 1;
     if (use_smem) {
         GF_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -53,7 +53,7 @@ GF_HD double gf_draw_dim(const gf_dev_model& m, int k, double u) {
  * prior tables are constant-bank operands and the word of the Philox block is a register, not a select
  * chain: +12 % on the unitary scan, +8 % on the x scan.  The BSM scan kernels keep the rolled loop: they sit
  * at the 128-register limit and the unrolled draws made them spill. */
-template <bool UNROLL = false>
+template <bool UNROLL = false, int NDIM = 0>
 GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, double* theta) {
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32);
@@ -62,8 +62,8 @@ GF_HD void gf_draw_theta(const gf_dev_model& m, uint64_t seed, uint64_t index, d
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-        for (int k = 0; k < GF_MAX_DIM; ++k) {
-            if (k >= m.ndim) break;
+        for (int k = 0; k < (NDIM > 0 ? NDIM : GF_MAX_DIM); ++k) {
+            if (NDIM == 0 && k >= m.ndim) break;
             const int j = k & 3;
             if (j == 0) r = gf_philox4x32_10(c0, c1, (uint32_t)(k >> 2), 0u, k0, k1);
             const uint32_t w = j == 0 ? r.x : j == 1 ? r.y : j == 2 ? r.z : r.w;

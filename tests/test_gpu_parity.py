@@ -484,6 +484,45 @@ def test_scan_samples_against_oracle(torch, mode):
         assert np.array_equal(h, ref_h)
 
 
+@pytest.mark.parametrize('mode', ['unitary', 'texture', 'anarchic'])
+def test_scan_column_map_kernels_on_permuted_layouts(torch, mode):
+    """The scan kernels have compile-time specialisations for the layouts scan.scan_paramset produces; any
+    other column order runs the column-map kernels.  Same checks on a model with its columns rotated:
+    compositions against the truth evaluator on the device-drawn sample, fused histogram bit-exact."""
+    from golemflavor_b200.enums import ParamTag
+    from golemflavor_b200.param import Param, ParamSet
+    pset = scan.scan_paramset(mode, 6)
+    n = len(pset)
+    cnt, seed = 20000, 11
+    if mode == 'unitary':      # one tag only (its order identifies the parameters): shift the columns by a spectator
+        pp = ParamSet([Param(name='spectator', value=0.5, ranges=[0., 1.], std=0.1, tag=ParamTag.NUISANCE)] + list(pset))
+        fm = scan.scan_model(mode, source_ratio=(1, 2, 0), paramset=pp)
+        theta_p, frs, st = scan.scan_samples(fm, cnt, seed=seed)
+        theta = theta_p[:, 1:]
+    else:                      # logLam first: the relative order within each tag is kept
+        perm = [n - 1] + list(range(n - 1))
+        pp = ParamSet([pset[k] for k in perm])
+        fm = scan.scan_model(mode, source_ratio=(1, 2, 0), dimension=6, texture=Texture.OET, paramset=pp)
+        theta_p, frs, st = scan.scan_samples(fm, cnt, seed=seed)
+        theta = np.empty_like(theta_p)
+        theta[:, perm] = theta_p                            # back to the canonical column order
+    lo, hi = np.array(pset.ranges).T
+    assert np.all(theta >= lo) and np.all(theta <= hi)
+    if mode == 'unitary':
+        ref = go.batch_u_to_fr(np.array([1, 2, 0.]) / 3, go.batch_angles_to_u(theta)).astype(float)
+    elif mode == 'texture':
+        ref = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], model.TEXTURE_ANGLES['OET'], theta[:, 6], 6,
+                                          models.BINNING, np.array([1, 2, 0.]) / 3)
+    else:
+        ref = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], theta[:, 6:10], theta[:, 10], 6,
+                                          models.BINNING, np.array([1, 2, 0.]) / 3)
+    assert np.abs(frs - ref).max() < FR_TOL
+    assert not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+    for nb in (25, 200):
+        h, kept = scan.scan_histogram(fm, cnt, nb=nb, seed=seed, distributed=False)
+        assert kept == cnt and np.array_equal(h, go.ternary_histogram(frs, nb))
+
+
 def test_scan_is_shard_and_geometry_invariant(torch):
     fm = scan.scan_model('unitary')
     n = 3_000_000
