@@ -88,12 +88,13 @@ struct gf_point {
  *                     produces; the texture scan is GF_SPEC_FIXED7.  The drawn sample stays in registers. */
 #define GF_SPEC_SM4 7
 #define GF_SPEC_NPFREE11 8
+#define GF_SPEC_SM5X 9 /* the x scan: columns 0-3 = the mixing coordinates, 4 = x with source (x, 1-x, 0), ndim = 5 */
 #undef GF_SPEC_IS_SM
-#define GF_SPEC_IS_SM(SPEC) ((SPEC) == GF_SPEC_SM || (SPEC) == GF_SPEC_SM6 || (SPEC) == GF_SPEC_SM4)
+#define GF_SPEC_IS_SM(SPEC) ((SPEC) == GF_SPEC_SM || (SPEC) == GF_SPEC_SM6 || (SPEC) == GF_SPEC_SM4 || (SPEC) == GF_SPEC_SM5X)
 #define GF_SPEC_IS_NPFREE(SPEC) ((SPEC) == GF_SPEC_NPFREE || (SPEC) == GF_SPEC_NPFREE11)
 #define GF_SPEC_STATIC_NDIM(SPEC)                                                                                  \
     ((SPEC) == GF_SPEC_SM6 ? 6 : (SPEC) == GF_SPEC_FIXED7 ? 7 : (SPEC) == GF_SPEC_FIXED12 ? 12 : (SPEC) == GF_SPEC_SM4 ? 4 : \
-     (SPEC) == GF_SPEC_NPFREE11 ? 11 : 0)
+     (SPEC) == GF_SPEC_NPFREE11 ? 11 : (SPEC) == GF_SPEC_SM5X ? 5 : 0)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
@@ -117,6 +118,17 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         q.src[0] = m.fixed_src[0];
         q.src[1] = m.fixed_src[1];
         q.src[2] = m.fixed_src[2];
+        return;
+    }
+    if (SPEC == GF_SPEC_SM5X) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        const double x = get(4); /* scripts/mc_x.py:187 */
+        q.src[0] = x;
+        q.src[1] = 1.0 - x;
+        q.src[2] = 0.0;
         return;
     }
     if (SPEC == GF_SPEC_NPFREE11) {
@@ -320,7 +332,11 @@ GF_HD int gf_model_scan_spec(const gf_dev_model& m) {
     const int spec = gf_model_spec(m);
     const bool sm03 = m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3;
     if (spec == GF_SPEC_SM6) return GF_SPEC_SM;
-    if (spec == GF_SPEC_SM) return (sm03 && m.ndim == 4 && gf_model_has_fixed_source(m)) ? GF_SPEC_SM4 : GF_SPEC_SM;
+    if (spec == GF_SPEC_SM) {
+        if (sm03 && m.ndim == 4 && gf_model_has_fixed_source(m)) return GF_SPEC_SM4;
+        if (sm03 && m.ndim == 5 && m.col_x == 4) return GF_SPEC_SM5X;
+        return GF_SPEC_SM;
+    }
     if (spec == GF_SPEC_FIXED12) return GF_SPEC_FIXED;
     if (spec == GF_SPEC_NPFREE) {
         const bool canon = sm03 && m.ndim == 11 && m.col_mass[0] == 4 && m.col_mass[1] == 5 && m.col_np[0] == 6 && m.col_np[1] == 7 &&

@@ -133,6 +133,7 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
      : spec == GF_SPEC_FIXED7   ? k_hist<SCAN, SMEM, GF_SPEC_FIXED7>                          \
      : spec == GF_SPEC_SM       ? k_hist<SCAN, SMEM, GF_SPEC_SM>                              \
      : spec == GF_SPEC_SM4      ? k_hist<SCAN, SMEM, GF_SPEC_SM4>                             \
+     : spec == GF_SPEC_SM5X     ? k_hist<SCAN, SMEM, GF_SPEC_SM5X>                            \
      : spec == GF_SPEC_NPFREE   ? k_hist<SCAN, SMEM, GF_SPEC_NPFREE>                          \
      : spec == GF_SPEC_NPFREE11 ? k_hist<SCAN, SMEM, GF_SPEC_NPFREE11>                        \
                                 : k_hist<SCAN, SMEM, GF_SPEC_GENERIC>)

@@ -484,7 +484,7 @@ def test_scan_samples_against_oracle(torch, mode):
         assert np.array_equal(h, ref_h)
 
 
-@pytest.mark.parametrize('mode', ['unitary', 'texture', 'anarchic'])
+@pytest.mark.parametrize('mode', ['unitary', 'x', 'texture', 'anarchic'])
 def test_scan_column_map_kernels_on_permuted_layouts(torch, mode):
     """The scan kernels have compile-time specialisations for the layouts scan.scan_paramset produces; any
     other column order runs the column-map kernels.  Same checks on a model with its columns rotated:
@@ -510,6 +510,9 @@ def test_scan_column_map_kernels_on_permuted_layouts(torch, mode):
     assert np.all(theta >= lo) and np.all(theta <= hi)
     if mode == 'unitary':
         ref = go.batch_u_to_fr(np.array([1, 2, 0.]) / 3, go.batch_angles_to_u(theta)).astype(float)
+    elif mode == 'x':
+        src = np.column_stack([theta[:, 4], 1 - theta[:, 4], np.zeros(cnt)])
+        ref = go.batch_u_to_fr(src, go.batch_angles_to_u(theta[:, :4])).astype(float)
     elif mode == 'texture':
         ref = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], model.TEXTURE_ANGLES['OET'], theta[:, 6], 6,
                                           models.BINNING, np.array([1, 2, 0.]) / 3)
