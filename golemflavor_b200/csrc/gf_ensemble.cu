@@ -18,7 +18,6 @@
  */
 #include <atomic>
 #include <cooperative_groups.h>
-#include <type_traits>
 
 #include "gf_common.cuh"
 #include "gf_ensemble_dev.cuh"
