@@ -131,10 +131,12 @@ class LnProb(object):
 
     def __call__(self, theta):
         batched = (theta.ndim if hasattr(theta, 'ndim') else np.ndim(theta)) > 1
-        out = self.evaluate(theta)
         if _is_tensor(theta):
+            out = self.evaluate(theta)
             return out if batched else out[0]
-        out = out.cpu().numpy()
+        # host data in, host data out: one C call (staging, H2D, kernel, D2H inside the library) -- for the
+        # emcee-sized batches of a host-side sampler the per-call latency is what counts
+        out = self.evaluate_host(theta)
         return out if batched else float(out[0])
 
 

@@ -1,0 +1,25 @@
+"""Per-call latency of the Python entry point for emcee-sized batches (host numpy in, numpy out)."""
+import os, sys, time, cProfile, pstats
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np, torch, models
+from golemflavor_b200 import llh
+from golemflavor_b200.enums import Texture
+g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+a2, as2, ps2 = models.notebook_model(g['asimov_angles'])
+f2 = llh.LnProb(a2, as2, ps2)
+a3, as3, ps3 = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
+f3 = llh.LnProb(a3, as3, ps3)
+rng = np.random.default_rng(1)
+for name, fn, ps, n in (('SM 512', f2, ps2, 512), ('BSM 2048', f3, ps3, 2048), ('SM 50', f2, ps2, 50)):
+    th = models.draw_in_ranges(ps, n, rng, seeds=True)
+    for _ in range(20): fn(th)
+    t0 = time.perf_counter()
+    for _ in range(2000): fn(th)
+    dt = (time.perf_counter() - t0) / 2000
+    print('%-9s %.1f us per call' % (name, dt * 1e6))
+th = models.draw_in_ranges(ps2, 512, rng, seeds=True)
+pr = cProfile.Profile(); pr.enable()
+for _ in range(2000): f2(th)
+pr.disable()
+pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
