@@ -38,6 +38,19 @@ def sweep_paramset(dimension):
         Param(name='logLam', value=float(np.mean(b)), ranges=[-101.0, float(b[1])], std=3, tag=ParamTag.SCALE)])
 
 
+_STREAMS = {}
+
+
+def _dim_stream(torch, dim):
+    """One side stream per (device, dimension), created once: torch's caching allocator keeps a pool per
+    stream, and a cold pool means a cudaMalloc -- which waits for every kernel already running and would
+    serialise the dimensions."""
+    key = (torch.cuda.current_device(), int(dim))
+    if key not in _STREAMS:
+        _STREAMS[key] = torch.cuda.Stream()
+    return _STREAMS[key]
+
+
 def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, source_ratio=(1, 2, 0),
           injected_ratio=(1, 1, 1), smearing=0.02, nwalkers=60, burnin=200, nsteps=1000, seed=25,
           binning=DEFAULT_BINNING, distributed=True):
@@ -73,7 +86,8 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
         p0 = np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)])
         np.random.set_state(state)
         p0[:, :, ndim - 1] = scales[:, None]                      # frozen column: identical in all walkers
-        stream = torch.cuda.Stream()
+        stream = _dim_stream(torch, dim)
+        stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
             sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, nchains=nchains, seed=seed + 1000 * dim, nfree=ndim - 1,
                                             chain0=idx[0])
