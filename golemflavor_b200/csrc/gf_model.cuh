@@ -99,62 +99,9 @@ struct gf_point {
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
 
-/* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
-template <int SPEC = GF_SPEC_GENERIC, class Get>
-GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
-    if (SPEC == GF_SPEC_SM6) {
-        q.sm[0] = get(0);
-        q.sm[1] = get(1);
-        q.sm[2] = get(2);
-        q.sm[3] = get(3);
-        gfp_angles_to_fr(get(4), get(5), q.src);
-        return;
-    }
-    if (SPEC == GF_SPEC_SM4) {
-        q.sm[0] = get(0);
-        q.sm[1] = get(1);
-        q.sm[2] = get(2);
-        q.sm[3] = get(3);
-        q.src[0] = m.fixed_src[0];
-        q.src[1] = m.fixed_src[1];
-        q.src[2] = m.fixed_src[2];
-        return;
-    }
-    if (SPEC == GF_SPEC_SM5X) {
-        q.sm[0] = get(0);
-        q.sm[1] = get(1);
-        q.sm[2] = get(2);
-        q.sm[3] = get(3);
-        const double x = get(4); /* scripts/mc_x.py:187 */
-        q.src[0] = x;
-        q.src[1] = 1.0 - x;
-        q.src[2] = 0.0;
-        return;
-    }
-    if (SPEC == GF_SPEC_NPFREE11) {
-        q.sm[0] = get(0);
-        q.sm[1] = get(1);
-        q.sm[2] = get(2);
-        q.sm[3] = get(3);
-        q.mass[0] = get(4);
-        q.mass[1] = get(5);
-        q.np[0] = get(6);
-        q.np[1] = get(7);
-        q.np[2] = get(8);
-        q.np[3] = get(9);
-        q.loglam = get(10);
-        return;
-    }
-    if (SPEC == GF_SPEC_FIXED7 || SPEC == GF_SPEC_FIXED12) {
-        q.sm[0] = get(0);
-        q.sm[1] = get(1);
-        q.sm[2] = get(2);
-        q.sm[3] = get(3);
-        q.mass[0] = get(4);
-        q.mass[1] = get(5);
-        q.loglam = get(SPEC == GF_SPEC_FIXED12 ? 11 : 6);
-        return;
-    }
+/* the general case: runtime column map */
+template <int SPEC, class Get>
+GF_HD void gf_resolve_point_mapped(const gf_dev_model& m, Get get, gf_point& q) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) q.sm[k] = m.col_sm[k] >= 0 ? get(m.col_sm[k]) : m.fixed_sm[k];
     if (SPEC != GF_SPEC_SM) {
@@ -185,6 +132,58 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
     }
 }
 
+/* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
+template <int SPEC = GF_SPEC_GENERIC, class Get>
+GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
+    if constexpr (SPEC == GF_SPEC_SM6) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        gfp_angles_to_fr(get(4), get(5), q.src);
+    } else if constexpr (SPEC == GF_SPEC_SM4) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.src[0] = m.fixed_src[0];
+        q.src[1] = m.fixed_src[1];
+        q.src[2] = m.fixed_src[2];
+    } else if constexpr (SPEC == GF_SPEC_SM5X) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        const double x = get(4); /* scripts/mc_x.py:187 */
+        q.src[0] = x;
+        q.src[1] = 1.0 - x;
+        q.src[2] = 0.0;
+    } else if constexpr (SPEC == GF_SPEC_NPFREE11) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.mass[0] = get(4);
+        q.mass[1] = get(5);
+        q.np[0] = get(6);
+        q.np[1] = get(7);
+        q.np[2] = get(8);
+        q.np[3] = get(9);
+        q.loglam = get(10);
+    } else if constexpr (SPEC == GF_SPEC_FIXED7 || SPEC == GF_SPEC_FIXED12) {
+        q.sm[0] = get(0);
+        q.sm[1] = get(1);
+        q.sm[2] = get(2);
+        q.sm[3] = get(3);
+        q.mass[0] = get(4);
+        q.mass[1] = get(5);
+        q.loglam = get(SPEC == GF_SPEC_FIXED12 ? 11 : 6);
+    } else {
+        gf_resolve_point_mapped<SPEC>(m, get, q);
+    }
+}
+
+
 /*
  * Measured flavor composition of one point.
  *   no_bsm : fr = u_to_fr(source, angles_to_u(sm))                (notebook SM model)
@@ -193,7 +192,7 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * The source normalisation 1/sum(s) and the 1/(E_max-E_min) factor cancel in the final
  * renormalisation and are not applied per bin.
  */
-/* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (Jacobi
+/* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (deflation
  * fallback), the transition in its four independent entries and the width-weighted sums. */
 template <int ILP, class TPART>
 GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
@@ -211,7 +210,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < ILP; ++i) ok = gfp_pencil_x4_fast(pp, pt, lam * m.g[b + i], x[i]) && ok;
-            if (!ok) { /* rare: Jacobi for whichever bin failed (re-tested: the flags are not kept in registers) */
+            if (!ok) { /* rare: refine whichever bin failed (re-tested: the flags are not kept in registers) */
 #pragma unroll
                 for (int i = 0; i < ILP; ++i) {
                     gfp_x4 again;

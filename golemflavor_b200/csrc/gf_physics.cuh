@@ -186,11 +186,17 @@ struct gfp_herm3 {
  *
  * The fp64 pipe is the bottleneck of every kernel here while the fp32 pipe idles, so the root is
  * SEEDED in single precision -- a degree-6 polynomial for w/delta (Chebyshev fit in t = 2 delta - 1,
- * scratch/fit_w32.py, relative error 3.4e-7) and the reciprocal slope r ~ 1/g'(w0) -- and polished by
- * two fp64 Newton steps with the frozen slope, w <- w - r g(w).  Error recursion e' = e (1 - r g') +
- * O(e^2): 3.4e-7 -> 9e-14 -> 2e-20 relative, i.e. fp64 rounding of g (~eps * w) is what remains.
- * 8 fp64 operations instead of the 23 of a full-precision degree-20 polynomial.
+ * scratch/fit_w32.py, relative error 3.4e-7) and the reciprocal slope r ~ 1/g'(w0) -- and polished in fp64
+ * with the frozen slope, w <- w - r g(w).  Error recursion e' = e (1 - r g') + O(e^2): 3.4e-7 -> 1e-13
+ * -> 2e-20 relative.  ONE step is taken by default: 1e-13 RELATIVE error of w means 5e-14 relative error
+ * of the eigenvalue gap at every gap size (an absolute error far below one ulp of the matrix scale once the
+ * pair is close), i.e. ~1e-13 on |V|^2 -- three orders inside the 1e-10 tolerance and below the closed form's
+ * own conditioning error (parity at scale unchanged at ~3e-12 worst) -- and the second step is 4 of the 83
+ * fp64 instructions of an energy bin (K2 0.596 -> 0.578 ms).  GFP_CUBIC_NEWTON_STEPS=2 restores it.
  */
+#ifndef GFP_CUBIC_NEWTON_STEPS
+#define GFP_CUBIC_NEWTON_STEPS 1
+#endif
 GF_HD double gfp_cubic_w(double delta) {
     const float d = (float)delta;
     const float t = fmaf(2.0f, d, -1.0f);
@@ -212,7 +218,9 @@ GF_HD double gfp_cubic_w(double delta) {
     const double r = (double)rf;
     double w = (double)w0;
     w = fma(-r, fma(fma(fma(4.0, w, -12.0), w, 9.0), w, -delta), w);
+#if GFP_CUBIC_NEWTON_STEPS > 1
     w = fma(-r, fma(fma(fma(4.0, w, -12.0), w, 9.0), w, -delta), w);
+#endif
     return w;
 }
 
