@@ -17,6 +17,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <type_traits>
 
 #include "gf_common.cuh"
 
@@ -31,14 +32,40 @@ extern std::atomic<unsigned long long> g_gf_launches;
 
 enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 
-template <int KIND, int SPEC>
+/* LAYOUT (compile-time layouts only): 0 = strided theta (runtime ld_point / ld_dim); 1 = contiguous rows
+ * (ld_dim == 1): every read is one load at a constant offset from the row pointer; 2 = packed rows of an even
+ * number of doubles on a 16-byte boundary: the row arrives in ndim/2 128-bit loads. */
+template <int KIND, int SPEC, int LAYOUT = 0>
 __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* __restrict__ row = th.p + i * th.ld_point;
-    if (SPEC == GF_SPEC_SM && KIND != GF_K_LNPRIOR) {
+    /* the point: prior + physics + likelihood on whatever `get` reads theta from */
+    auto evaluate = [&](auto get, auto ilp) {
+        constexpr int ILP = decltype(ilp)::value;
+        if (KIND == GF_K_LNPRIOR) {
+            lnp[i] = gf_point_lnprior(m, get);
+            return;
+        }
+        double fr[3];
+        unsigned st = 0u;
+        if (KIND == GF_K_FR) {
+            gf_point q;
+            gf_resolve_point<SPEC>(m, get, q);
+            st = gf_point_fr<SPEC, ILP>(m, q, fr);
+        } else {
+            lnp[i] = gf_point_lnprob<SPEC, ILP>(m, get, fr, st);
+        }
+        if (fr_out) {
+            fr_out[3 * i] = fr[0];
+            fr_out[3 * i + 1] = fr[1];
+            fr_out[3 * i + 2] = fr[2];
+        }
+        if (status) status[i] = (uint8_t)st;
+    };
+    if constexpr (SPEC == GF_SPEC_SM && KIND != GF_K_LNPRIOR) {
         /* SM-only models are bound by instruction issue, and a third of their instructions were 64-bit
          * address arithmetic of theta reads through the runtime column map (every value is read twice: by
          * the prior loop and by the physics).  Stage the point's row ONCE in shared memory, column-major
@@ -48,46 +75,51 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_L
         const double* src = row;
         /* left to the compiler's default unrolling: forcing it fully (or not at all) costs the SoA layout 40 % */
         for (int k = 0; k < m.ndim; ++k, src += th.ld_dim) sh_theta[k * GF_LP_THREADS + threadIdx.x] = __ldg(src);
-        auto get = [&](int k) { return sh_theta[k * GF_LP_THREADS + threadIdx.x]; };
-        double fr[3];
-        unsigned st = 0u;
-        if (KIND == GF_K_FR) {
-            gf_point q;
-            gf_resolve_point<SPEC>(m, get, q);
-            st = gf_point_fr<SPEC, 1>(m, q, fr);
-        } else {
-            lnp[i] = gf_point_lnprob<SPEC, 1>(m, get, fr, st);
+        evaluate([&](int k) { return sh_theta[k * GF_LP_THREADS + threadIdx.x]; }, std::integral_constant<int, 1>{});
+    } else if constexpr (LAYOUT == 2) {
+        constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC);
+        static_assert(ND > 0 && ND % 2 == 0, "LAYOUT 2 needs a compile-time layout with an even number of columns");
+        double v[ND];
+        const double2* __restrict__ r2 = reinterpret_cast<const double2*>(row);
+#pragma unroll
+        for (int k = 0; k < ND / 2; ++k) {
+            const double2 t = __ldg(r2 + k);
+            v[2 * k] = t.x;
+            v[2 * k + 1] = t.y;
         }
-        if (fr_out) {
-            fr_out[3 * i] = fr[0];
-            fr_out[3 * i + 1] = fr[1];
-            fr_out[3 * i + 2] = fr[2];
-        }
-        if (status) status[i] = (uint8_t)st;
-        return;
-    }
-    /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform; for
-     * GF_SPEC_SM6 every k is a compile-time constant and repeated reads of a column are one load) */
-    auto get = [&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); };
-    if (KIND == GF_K_LNPRIOR) {
-        lnp[i] = gf_point_lnprior(m, get);
-        return;
-    }
-    double fr[3];
-    unsigned st = 0u;
-    if (KIND == GF_K_FR) {
-        gf_point q;
-        gf_resolve_point<SPEC>(m, get, q);
-        st = gf_point_fr<SPEC, 2>(m, q, fr);
+        evaluate([&](int k) { return v[k]; }, std::integral_constant<int, 2>{});
+    } else if constexpr (LAYOUT == 1) {
+        evaluate([&](int k) { return __ldg(row + k); }, std::integral_constant<int, 2>{});
     } else {
-        lnp[i] = gf_point_lnprob<SPEC, 2>(m, get, fr, st);
+        /* one 64-bit multiply for the row, then a warp-uniform offset per column (k and ld_dim are uniform;
+         * with a compile-time layout every k is a constant and repeated reads of a column are one load) */
+        evaluate([&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); }, std::integral_constant<int, 2>{});
     }
-    if (fr_out) {
-        fr_out[3 * i] = fr[0];
-        fr_out[3 * i + 1] = fr[1];
-        fr_out[3 * i + 2] = fr[2];
+}
+
+/* one launch of k_lnprob: specialisation from the model, theta layout from the view */
+template <int KIND>
+static void launch_lnprob(const gf_dev_model& d, int spec, const gf_theta_view& th, int64_t n, double* d_lnp, double* d_fr, uint8_t* d_status,
+                          cudaStream_t stream) {
+    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS);
+    const bool rows = th.ld_dim == 1;
+    const bool packed16 = rows && th.ld_point == d.ndim && (reinterpret_cast<uintptr_t>(th.p) & 15u) == 0;
+#define GF_LP_LAUNCH(SPEC, LAYOUT, SMEM) k_lnprob<KIND, SPEC, LAYOUT><<<blocks, GF_LP_THREADS, SMEM, stream>>>(d, th, n, d_lnp, d_fr, d_status)
+    switch (spec) {
+        case GF_SPEC_FIXED: GF_LP_LAUNCH(GF_SPEC_FIXED, 0, 0); break;
+        case GF_SPEC_FIXED7:
+            if (rows) GF_LP_LAUNCH(GF_SPEC_FIXED7, 1, 0); else GF_LP_LAUNCH(GF_SPEC_FIXED7, 0, 0);
+            break;
+        case GF_SPEC_FIXED12:
+            if (packed16) GF_LP_LAUNCH(GF_SPEC_FIXED12, 2, 0); else if (rows) GF_LP_LAUNCH(GF_SPEC_FIXED12, 1, 0); else GF_LP_LAUNCH(GF_SPEC_FIXED12, 0, 0);
+            break;
+        case GF_SPEC_SM: GF_LP_LAUNCH(GF_SPEC_SM, 0, (size_t)d.ndim * GF_LP_THREADS * sizeof(double)); break;
+        case GF_SPEC_SM6:
+            if (packed16) GF_LP_LAUNCH(GF_SPEC_SM6, 2, 0); else if (rows) GF_LP_LAUNCH(GF_SPEC_SM6, 1, 0); else GF_LP_LAUNCH(GF_SPEC_SM6, 0, 0);
+            break;
+        default: GF_LP_LAUNCH(GF_SPEC_GENERIC, 0, 0); break; /* GENERIC, and NPFREE (a scan-only specialisation) */
     }
-    if (status) status[i] = (uint8_t)st;
+#undef GF_LP_LAUNCH
 }
 
 static int check_view(const char* fn, const gf_model* model, const double* d_theta, int64_t n, int64_t ld_point, int64_t ld_dim) {
@@ -106,20 +138,8 @@ static int launch(const char* fn, const gf_model* model, const double* d_theta, 
     if (int rc = check_view(fn, model, d_theta, n, ld_point, ld_dim)) return rc;
     if (n == 0) return GF_OK;
     const gf_theta_view th{d_theta, ld_point, ld_dim};
-    const int spec = KIND == GF_K_LNPRIOR ? GF_SPEC_GENERIC : gf_model_spec(d); /* NPFREE falls through to GENERIC */
-    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS);
-    if (spec == GF_SPEC_FIXED)
-        k_lnprob<KIND, GF_SPEC_FIXED><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
-    else if (spec == GF_SPEC_FIXED7)
-        k_lnprob<KIND, GF_SPEC_FIXED7><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
-    else if (spec == GF_SPEC_FIXED12)
-        k_lnprob<KIND, GF_SPEC_FIXED12><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
-    else if (spec == GF_SPEC_SM)
-        k_lnprob<KIND, GF_SPEC_SM><<<blocks, GF_LP_THREADS, (size_t)d.ndim * GF_LP_THREADS * sizeof(double), stream>>>(d, th, n, d_lnp, d_fr, d_status);
-    else if (spec == GF_SPEC_SM6)
-        k_lnprob<KIND, GF_SPEC_SM6><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
-    else
-        k_lnprob<KIND, GF_SPEC_GENERIC><<<blocks, GF_LP_THREADS, 0, stream>>>(d, th, n, d_lnp, d_fr, d_status);
+    const int spec = KIND == GF_K_LNPRIOR ? GF_SPEC_GENERIC : gf_model_spec(d);
+    launch_lnprob<KIND>(d, spec, th, n, d_lnp, d_fr, d_status, stream);
     ++g_gf_launches;
     GF_LAUNCH_CHECK(fn);
     return GF_OK;
@@ -248,25 +268,7 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
         }
         GF_CUDA(cudaMemcpyAsync(p.d_theta[s], src, cnt * ndim * sizeof(double), cudaMemcpyHostToDevice, p.stream[s]));
         const gf_theta_view th{p.d_theta[s], ndim, 1};
-        const int spec = gf_model_spec(d);
-        if (spec == GF_SPEC_FIXED)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
-        else if (spec == GF_SPEC_FIXED7)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED7><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
-        else if (spec == GF_SPEC_FIXED12)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_FIXED12><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
-        else if (spec == GF_SPEC_SM)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_SM><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, (size_t)ndim * GF_LP_THREADS * sizeof(double), p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
-        else if (spec == GF_SPEC_SM6)
-            k_lnprob<GF_K_LNPROB, GF_SPEC_SM6><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
-        else
-            k_lnprob<GF_K_LNPROB, GF_SPEC_GENERIC><<<gf_blocks_for(cnt, GF_LP_THREADS), GF_LP_THREADS, 0, p.stream[s]>>>(
-                d, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr);
+        launch_lnprob<GF_K_LNPROB>(d, gf_model_spec(d), th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr, p.stream[s]);
         ++g_gf_launches;
         GF_LAUNCH_CHECK("gf_lnprob_host");
         GF_CUDA(cudaMemcpyAsync(direct ? h_lnprob + off : p.s_lnp[s], p.d_lnp[s], cnt * sizeof(double), cudaMemcpyDeviceToHost, p.stream[s]));

@@ -7,6 +7,7 @@ composition (== 1e-10 relative to its norm), log-likelihood / log-posterior with
 histogram counts bit-exact given identical samples."""
 
 import argparse
+import ctypes as C
 import os
 import sys
 
@@ -261,6 +262,38 @@ def test_sm_only_column_layouts_agree(torch, golden):
     ref = go.batch_lnprior(theta, lo, hi, kind, list(pset.nominal_values), [p.std or 1.0 for p in pset]) + \
         go.batch_multi_gaussian(ref_fr, go.angles_to_fr(g['asimov_angles']), 0.02)
     assert np.max(np.abs(a[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+
+
+def test_theta_memory_layouts_through_the_c_abi(torch, golden):
+    """The compile-time column layouts pick their loads from the theta view: 128-bit loads for packed,
+    16-byte aligned rows of an even length, scalar loads at constant offsets for contiguous rows, strided
+    loads otherwise.  Same values from every view of the same data, straight through gf_lnprob."""
+    g = golden('ref_llh.npz')
+    lib = _lib.load()
+    rng = np.random.default_rng(31)
+    cases = [models.notebook_model(g['asimov_angles']),                                  # 6 columns (SM6)
+             models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OUT)]       # 7 columns (FIXED7)
+    for args, asimov, pset in cases:
+        fn = llh.LnProb(args, asimov, pset)
+        nd, n = fn.ndim, 3001
+        theta = torch.as_tensor(models.draw_in_ranges(pset, n, rng)).cuda()
+
+        def run(ptr_tensor, offset, ld_point, ld_dim):
+            out = torch.empty(n, dtype=torch.float64, device='cuda')
+            _lib.check(lib.gf_lnprob(fn.model.ref, C.c_void_p(ptr_tensor.data_ptr() + 8 * offset), n, ld_point, ld_dim, _lib.ptr(out),
+                                     None, None, _lib.stream_ptr(torch)))
+            return out.cpu().numpy()
+
+        ref = run(theta, 0, nd, 1)                                  # packed rows, 256-byte aligned base
+        buf = torch.zeros(nd * n + 1, dtype=torch.float64, device='cuda')
+        buf[1:] = theta.reshape(-1)
+        assert np.array_equal(run(buf, 1, nd, 1), ref)              # packed rows on an 8-byte boundary only
+        wide = torch.zeros((n, nd + 3), dtype=torch.float64, device='cuda')
+        wide[:, :nd] = theta
+        assert np.array_equal(run(wide, 0, nd + 3, 1), ref)         # padded rows
+        soa = theta.t().contiguous()
+        assert np.array_equal(run(soa, 0, 1, n), ref)               # column-major
+        assert np.isfinite(ref).mean() > 0.5 and not np.isnan(ref).any()
 
 
 def test_bsm_fixed_texture_column_layouts_agree(torch, golden):
