@@ -87,7 +87,11 @@ GF_HD double gfp_rsqrt(double x) {
  * (negative -> NaN like the reference's sqrt, fr.py:146-152). */
 GF_HD double gfp_sqrt01(double x) {
 #ifdef __CUDA_ARCH__
-    if (x > 1e-290 && x < 1e290) return x * gfp_rsqrt(x);
+    /* 1e-290 < x < 1e290 tested on the exponent field with integer instructions (two fp64 compares would
+     * sit on the pipe every kernel here is bound by): the unsigned subtraction sends negative numbers,
+     * zeros, subnormals, infinities and NaNs to the library path in one comparison */
+    const unsigned hi = (unsigned)__double2hiint(x);
+    if (hi - 0x03D00000u < 0x7C200000u - 0x03D00000u) return x * gfp_rsqrt(x); /* 2^-962 <= x < 2^963 */
 #endif
     return sqrt(x);
 }
