@@ -49,7 +49,9 @@
 
 /* Relative eigenvalue gap (in units of 2 sqrt(Q)) below which the closed-form path hands over
  * to Jacobi: the closed form loses accuracy like eps/gap^2, Jacobi like eps/gap. */
-#ifndef GFP_FAST_MIN_SIN2
+#ifdef GFP_FAST_MIN_SIN2
+#define GFP_FAST_MIN_SIN2_OVERRIDDEN 1 /* developer builds with another threshold use the fp64 compare */
+#else
 #define GFP_FAST_MIN_SIN2 1.4e-6 /* sin^2(phi/3): gap = sqrt(3 * sin^2) ~ 2.0e-3 */
 #endif
 #define GFP_ILL_GAP 1e-6
@@ -270,8 +272,15 @@ GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, d
     out.x10 = n10 * i0;
     out.x01 = n01 * i1;
     out.x11 = n11 * i1;
-    /* Q > tiny also rejects NaN; s2 >= limit rejects close pairs, NaN and negative round-off */
+    /* Q > tiny also rejects NaN; s2 >= limit rejects close pairs, NaN and negative round-off.  On the device
+     * both tests read the exponent fields with integer instructions (unsigned range checks: positive, finite,
+     * above the threshold's high word) instead of two compares on the fp64 pipe. */
+#if defined(__CUDA_ARCH__) && !defined(GFP_FAST_MIN_SIN2_OVERRIDDEN)
+    const unsigned hq = (unsigned)__double2hiint(Q), hs = (unsigned)__double2hiint(s2);
+    return (hq - 0x05E00000u < 0x7FF00000u - 0x05E00000u) && (hs - 0x3EB77CF4u < 0x7FF00000u - 0x3EB77CF4u); /* Q > ~1e-280, s2 >= 1.4e-6 */
+#else
     return (Q > 1e-280) && (s2 >= GFP_FAST_MIN_SIN2);
+#endif
 }
 
 /* Invariants of one matrix computed directly (single-matrix entry points and tests). */
