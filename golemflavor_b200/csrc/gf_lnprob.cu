@@ -6,13 +6,15 @@
  * One parameter point per thread; the flattened model travels as a __grid_constant__ kernel
  * parameter (constant bank), theta is read through a strided view so that both the emcee
  * row-major layout and an SoA layout are served, everything else stays in registers.
- * The kernel is fp64-pipe bound (~2.5e3 DFMA-pipe instructions per point for 20 energy bins
- * against 64 B of traffic), see DESIGN.md.  theta is loaded directly (no shared-memory staging):
- * an A/B test of a persistent-grid variant that double-buffered theta tiles through shared memory
- * with cp.async was 1-12 % SLOWER the coarser its work granularity (0.787 ms at one 32-point tile
- * per warp ... 0.874 ms fully persistent, vs 0.780 ms here) -- the exposed first-load latency is
- * covered by other warps' arithmetic, while the hardware block scheduler's fine-grained dynamic
- * balancing over SMs is worth more than the prefetch.
+ * The BSM kernel is fp64-pipe bound (~1.9e3 fp64-pipe instructions per point for 20 energy bins
+ * against 64 B of traffic), see DESIGN.md.  The kernels are specialised at compile time on the model
+ * (gf_model_spec: which quantities are sampled, and -- for the reference's own column layouts -- where)
+ * and on the theta view (LAYOUT).  theta is loaded directly by the BSM kernels (no shared-memory
+ * staging): an A/B test of a persistent-grid variant that double-buffered theta tiles through shared
+ * memory with cp.async was 1-12 % SLOWER the coarser its work granularity (0.787 ms at one 32-point
+ * tile per warp ... 0.874 ms fully persistent, vs 0.780 ms at the time) -- the exposed first-load
+ * latency is covered by other warps' arithmetic, while the hardware block scheduler's fine-grained
+ * dynamic balancing over SMs is worth more than the prefetch.
  */
 #include <atomic>
 #include <mutex>
