@@ -170,7 +170,10 @@ extern "C" int gf_lnprior(const gf_model* model, const double* d_theta, int64_t 
 namespace {
 
 constexpr int kSlots = 3;               /* H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c */
-constexpr int64_t kChunkPoints = 1 << 18;
+#ifndef GF_HOST_CHUNK_LOG2
+#define GF_HOST_CHUNK_LOG2 18
+#endif
+constexpr int64_t kChunkPoints = 1ll << GF_HOST_CHUNK_LOG2;
 
 struct HostPipe {
     int device = -1;
