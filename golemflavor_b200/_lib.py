@@ -102,6 +102,7 @@ _SIGNATURES = {
     'gf_ensemble_run': (C.c_int, [C.POINTER(Model), C.POINTER(EnsembleConfig), _P, _P, _P, _P, _P, _P]),
     'gf_selftest_math': (C.c_int, [_P, C.c_int64, _P, _P, _P]),
     'gf_selftest_trig': (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
+    'gf_selftest_log': (C.c_int, [_P, C.c_int64, _P, _P]),
     'gf_fp64_peak_probe': (C.c_int, [C.c_int32, C.c_int64, _P, C.POINTER(C.c_double), _P]),
 }
 EXPORTS = tuple(sorted(_SIGNATURES))

@@ -374,7 +374,22 @@ __global__ void __launch_bounds__(GF_EW_THREADS)
     cs_only[i] = gfp_cos(x[i]);
 }
 
+__global__ void __launch_bounds__(GF_EW_THREADS) k_selftest_log(const double* __restrict__ x, int64_t n, double* __restrict__ lg) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lg[i] = gfp_log_pos(x[i]);
+}
+
 /* ------------------------------------------------------------------ C ABI */
+
+extern "C" int gf_selftest_log(const double* d_x, int64_t n, double* d_log, void* stream) {
+    GF_REQUIRE(n >= 0, "gf_selftest_log: n = %lld", (long long)n);
+    if (n == 0) return GF_OK;
+    GF_REQUIRE(d_x && d_log, "gf_selftest_log: null pointer");
+    k_selftest_log<<<gf_blocks_for(n, GF_EW_THREADS), GF_EW_THREADS, 0, (cudaStream_t)stream>>>(d_x, n, d_log);
+    ++g_gf_launches;
+    GF_LAUNCH_CHECK("k_selftest_log");
+    return GF_OK;
+}
 
 extern "C" int gf_selftest_trig(const double* d_x, int64_t n, double* d_sin, double* d_cos, double* d_cos_only, void* stream) {
     GF_REQUIRE(n >= 0, "gf_selftest_trig: n = %lld", (long long)n);

@@ -69,8 +69,8 @@ GF_HD double gf_ens_z(const gf_ens_args& A, double u) {
 /* the arithmetic on the draws that does not depend on any walker position */
 GF_HD void gf_ens_finish_draw(const gf_ens_args& A, gf_ens_draw& dr) {
     dr.z = gf_ens_z(A, dr.u_z);
-    dr.lz = (double)(A.nfree - 1) * log(dr.z);
-    dr.lu = log(dr.u_accept);
+    dr.lz = (double)(A.nfree - 1) * gfp_log_pos(dr.z); /* z in [1/a, a], u in (0, 1): positive and normal */
+    dr.lu = gfp_log_pos(dr.u_accept);
 }
 
 /* q = c_j - z (c_j - p), contraction-free */

@@ -267,6 +267,9 @@ int gf_selftest_math(const double* d_x, int64_t n, double* d_rsqrt_out, double* 
 /* Device self-test of the table-free sin / cos of the CP phase (fr.py:157-159 evaluates them with NumPy):
  * sin_out, cos_out from the joint routine, cos_only_out from the cosine-only one. */
 int gf_selftest_trig(const double* d_x, int64_t n, double* d_sin_out, double* d_cos_out, double* d_cos_only_out, void* stream);
+/* Device self-test of the table-free logarithm of the sampler's acceptance test: log_out[i] ~ ln x[i] for
+ * positive normal x. */
+int gf_selftest_log(const double* d_x, int64_t n, double* d_log_out, void* stream);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t gf_launch_count(void);
 

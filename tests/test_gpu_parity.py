@@ -75,6 +75,16 @@ def test_device_trig_helpers(torch):
     assert np.max(np.abs(cs.cpu().numpy()[small] - np.cos(xl[small]))) < 4.5e-16
     assert np.max(np.abs(co.cpu().numpy()[small] - np.cos(xl[small]))) < 4.5e-16
     assert np.allclose(sn.cpu().numpy()[~small], np.sin(x[~small]), atol=1e-15) and np.allclose(co.cpu().numpy()[~small], np.cos(x[~small]), atol=1e-15)
+    # the sampler's logarithm: below 2 ulp on (0, 1), on the stretch factors [1/2, 2] and on the whole normal range
+    w = rng.integers(0, 1 << 32, 300000, dtype=np.uint64)
+    xs = np.concatenate([(w.astype(np.float64) + 0.5) / 4294967296.0, rng.uniform(0.5, 2.0, 100000), 10.0 ** rng.uniform(-300, 300, 100000),
+                         [1.0, 2.0, 0.5, np.e, 0.7071067811865476, 1.4142135623730951]])
+    xt2 = torch.as_tensor(xs).cuda()
+    lg = torch.empty_like(xt2)
+    _lib.check(_lib.load().gf_selftest_log(_lib.ptr(xt2), len(xs), _lib.ptr(lg), _lib.stream_ptr(torch)))
+    ref = np.log(xs.astype(np.longdouble))
+    assert np.max(np.abs(lg.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1e-300) * (ref != 0)) < 4.5e-16
+    assert lg.cpu().numpy()[np.where(xs == 1.0)[0][0]] == 0.0
     bad = torch.as_tensor(np.array([np.nan, np.inf, -np.inf])).cuda()
     _lib.check(_lib.load().gf_selftest_trig(_lib.ptr(bad), 3, _lib.ptr(sn), _lib.ptr(cs), _lib.ptr(co), _lib.stream_ptr(torch)))
     assert np.all(np.isnan(sn.cpu().numpy()[:3])) and np.all(np.isnan(cs.cpu().numpy()[:3])) and np.all(np.isnan(co.cpu().numpy()[:3]))
