@@ -122,16 +122,40 @@ def evidence_grid(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.O
     frozen at the grid value, ``lnZ = ln mean(L)``.  Returns ``{dimension: array[segments, 2]}`` like the
     reference's ``evidence_arr``; Bayes factors against the null point (scale -100) follow by subtraction
     (``plot.get_limit``, ``plot.py:149-213``)."""
-    from .scan import scan_evidence
+    import ctypes as C
+    torch = _lib.torch_cuda()
+    dist = _dist()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     src = np.asarray(source_ratio, dtype=np.float64)
     inj = np.asarray(injected_ratio, dtype=np.float64)
+    grid = [(int(d), float(s)) for d in dimensions for s in scale_grid(d, segments)]
+    # every grid point is one asynchronous launch into its own (max, sum-exp) slot; the model of a dimension is
+    # flattened once and only its frozen scale changes; one read-back (and one pair of all-reduces) at the end
+    lse = torch.empty((len(grid), 2), dtype=torch.float64, device='cuda')
+    lse[:, 0] = -np.inf
+    lse[:, 1] = 0.0
+    start, n = shard_range(samples, rank, world)
+    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=0)
+    lib, stream, base = _lib.load(), _lib.stream_ptr(torch), lse.data_ptr()
+    models = {}
+    for i, (dim, scale) in enumerate(grid):
+        if dim not in models:
+            args = Namespace(source_ratio=src / src.sum(), dimension=dim, texture=texture, binning=np.asarray(binning),
+                             no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing), fixed_scale=scale)
+            models[dim] = _model.flatten(args, None, ParamSet(sm_paramset(with_mass=True)))
+        fm = models[dim]
+        fm.struct.fixed_loglam = scale
+        _lib.check(lib.gf_scan_evidence(fm.ref, C.byref(cfg), C.c_void_p(base + 16 * i), stream))
+    if dist and world > 1:
+        gmax = lse[:, 0].clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        part = torch.where(torch.isfinite(gmax), lse[:, 1] * torch.exp(lse[:, 0] - gmax), torch.zeros_like(gmax))
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        lse = torch.stack([gmax, part], dim=1)
+    h = lse.cpu().numpy()
+    with np.errstate(divide='ignore'):
+        lnz = np.where(h[:, 1] > 0, h[:, 0] + np.log(h[:, 1]) - np.log(samples), -np.inf)
     out = {}
-    for dim in dimensions:
-        rows = []
-        for scale in scale_grid(dim, segments):
-            args = Namespace(source_ratio=src / src.sum(), dimension=int(dim), texture=texture, binning=np.asarray(binning),
-                             no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing), fixed_scale=float(scale))
-            fm = _model.flatten(args, None, ParamSet(sm_paramset(with_mass=True)))
-            rows.append((scale, scan_evidence(fm, samples, seed=seed)))
-        out[int(dim)] = np.array(rows)
-    return out
+    for (dim, scale), z in zip(grid, lnz):
+        out.setdefault(int(dim), []).append((scale, z))
+    return {d: np.array(rows) for d, rows in out.items()}
