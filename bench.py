@@ -364,6 +364,12 @@ def run_gpu(opts):
         cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
                                      'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
                                      'sharding': 'grid points split over %d rank(s), one all-reduce of the summaries' % world}
+        sens.evidence_grid(dimensions=(6,), segments=4, samples=10000)                 # warm-up
+        sec, ev = timed(lambda: sens.evidence_grid(segments=100, samples=1000000))
+        cfg_info['C5_evidence_grid'] = {'grid_points': int(sum(len(v) for v in ev.values())), 'samples_per_point': 1000000, 'seconds': sec,
+                                        'samples_per_s': 6e8 / sec,
+                                        'note': 'Monte-Carlo evidence ln mean(L) per (dimension, scale), what scripts/sens.py gets from MultiNest; '
+                                                'samples sharded over the ranks, two all-reduces of the 600 (max, sum-exp) slots'}
 
     if rank == 0:
         base = None
