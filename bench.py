@@ -282,94 +282,108 @@ def run_gpu(opts):
     finite_frac = float(np.isfinite(out_np).mean())
 
     # -- secondary: sharded Monte-Carlo scan with the histogram all-reduce (config 4)
-    scan_info = None
-    if opts.scan_samples > 0:
-        fm = scan.scan_model(opts.scan_mode, dimension=6)
-        scan.scan_histogram(fm, 10 ** 7, nb=25, seed=26)      # warm-up (also NCCL channel set-up)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        hist, kept = scan.scan_histogram(fm, opts.scan_samples, nb=25, seed=26, return_tensor=True)
-        s1.record()
-        barrier()
-        scan_ms = max_over_ranks(s0.elapsed_time(s1))
-        scan_info = {'mode': opts.scan_mode, 'samples': opts.scan_samples, 'nb': 25, 'seconds': scan_ms * 1e-3,
-                     'samples_per_s': opts.scan_samples / (scan_ms * 1e-3), 'scaling': 'strong',
-                     'kept': int(kept.item()), 'hist_checksum': int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item()),
-                     'collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
+    def _scan_section():
+        scan_info = None
+        if opts.scan_samples > 0:
+            fm = scan.scan_model(opts.scan_mode, dimension=6)
+            scan.scan_histogram(fm, 10 ** 7, nb=25, seed=26)      # warm-up (also NCCL channel set-up)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            hist, kept = scan.scan_histogram(fm, opts.scan_samples, nb=25, seed=26, return_tensor=True)
+            s1.record()
+            barrier()
+            scan_ms = max_over_ranks(s0.elapsed_time(s1))
+            scan_info = {'mode': opts.scan_mode, 'samples': opts.scan_samples, 'nb': 25, 'seconds': scan_ms * 1e-3,
+                         'samples_per_s': opts.scan_samples / (scan_ms * 1e-3), 'scaling': 'strong',
+                         'kept': int(kept.item()), 'hist_checksum': int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item()),
+                         'collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
+        return scan_info
+
+    try:
+        scan_info = _scan_section()
+    except Exception as exc:  # noqa: BLE001  (a secondary section must never cost the headline line)
+        scan_info = {'error': repr(exc)}
 
     # -- secondary: the sampler-shaped configs of BASELINE.json (latency-bound by design: 512 / 2048 /
     #    18000 points per half-step), run on the device-resident ensemble sampler
-    cfg_info = None
-    if opts.configs:
-        import models as _m
-        from golemflavor_b200 import mcmc, sens
-        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
-        cfg_info = {}
+    def _configs_section():
+        cfg_info = None
+        if opts.configs:
+            import models as _m
+            from golemflavor_b200 import mcmc, sens
+            g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+            cfg_info = {}
 
-        def timed(fn_):
-            barrier()
-            t0_ = time.perf_counter()
-            r_ = fn_()
+            def timed(fn_):
+                barrier()
+                t0_ = time.perf_counter()
+                r_ = fn_()
+                torch.cuda.synchronize()
+                return max_over_ranks(time.perf_counter() - t0_), r_
+
+            a2, as2, ps2 = _m.notebook_model(g['asimov_angles'])
+            f2 = llh.LnProb(a2, as2, ps2)
+            np.random.seed(25)
+            p0 = mcmc.flat_seed(ps2, 1024)
+            p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
+            # K1: the SM-only log-posterior (161 algorithmic FLOP / 56 B per point) is HBM-bound: report it against HBM
+            n1 = 1 << 24
+            th1 = torch.as_tensor(_m.draw_in_ranges(ps2, 1 << 20, np.random.default_rng(3))).cuda().repeat(16, 1)
+            o1 = torch.empty(n1, dtype=torch.float64, device='cuda')
+            k1 = lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(th1), n1, 6, 1, _lib.ptr(o1), None, None, stream))
+            for _ in range(3):
+                k1()
             torch.cuda.synchronize()
-            return max_over_ranks(time.perf_counter() - t0_), r_
+            k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0e.record()
+            for _ in range(20):
+                k1()
+            k1e.record()
+            torch.cuda.synchronize()
+            k1ms = k0e.elapsed_time(k1e) / 20
+            cfg_info['K1_sm_lnprob'] = {'points': n1, 'ms': k1ms, 'evals_per_s': n1 / (k1ms * 1e-3), 'bound': 'hbm',
+                                        'achieved_gbs': 56.0 * n1 / (k1ms * 1e-3) / 1e9,
+                                        'note': '6-D notebook model (4 PMNS coords + 2 source angles), theta 805 MB > L2'}
+            del th1, o1
+            smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
+            smp.run_mcmc(p0, 200, store=False)
+            sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))
+            cfg_info['C2_emcee_sm_fit'] = {'walkers': 1024, 'steps': 10000, 'ndim': 6, 'seconds': sec, 'evals_per_s': 1024 * 1e4 / sec,
+                                           'acceptance': float(np.mean(smp.acceptance_fraction)), 'launches': 1,
+                                           'note': 'replicas only: every rank runs the same chain shape independently'}
+            # C1: the reference's own CPU-sized case (3 raw source ratios, fixed NuFIT PMNS), here on the device sampler
+            a1, as1, ps1 = _m.sm_fit_c1(g['asimov_angles'])
+            f1 = llh.LnProb(a1, as1, ps1)
+            p1 = mcmc.flat_seed(ps1, 100)
+            smp1 = mcmc.DeviceEnsembleSampler(100, 3, f1, seed=25)
+            smp1.run_mcmc(p1, 100, store=False)
+            sec, _ = timed(lambda: smp1.run_mcmc(None, 1000, store=True, return_tensor=True))
+            cfg_info['C1_sm_fit_fixed_pmns'] = {'walkers': 100, 'steps': 1000, 'ndim': 3, 'seconds': sec, 'evals_per_s': 100 * 1000 / sec,
+                                                'acceptance': float(np.mean(smp1.acceptance_fraction)), 'launches': 1}
+            p3 = mcmc.flat_seed(pset, 4096)
+            smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
+            smp3.run_mcmc(p3, 100, store=False)
+            sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
+            cfg_info['C3_bsm_dim6_fit'] = {'walkers': 4096, 'steps': 2000, 'ndim': fn.ndim, 'seconds': sec, 'evals_per_s': 4096 * 2000 / sec,
+                                           'acceptance': float(np.mean(smp3.acceptance_fraction))}
+            sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first cooperative launches, NCCL float64 path)
+            sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
+            cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
+                                         'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
+                                         'sharding': 'grid points split over %d rank(s), one all-reduce of the summaries' % world}
+            sens.evidence_grid(dimensions=(6,), segments=4, samples=10000)                 # warm-up
+            sec, ev = timed(lambda: sens.evidence_grid(segments=100, samples=1000000))
+            cfg_info['C5_evidence_grid'] = {'grid_points': int(sum(len(v) for v in ev.values())), 'samples_per_point': 1000000, 'seconds': sec,
+                                            'samples_per_s': 6e8 / sec,
+                                            'note': 'Monte-Carlo evidence ln mean(L) per (dimension, scale), what scripts/sens.py gets from MultiNest; '
+                                                    'samples sharded over the ranks, two all-reduces of the 600 (max, sum-exp) slots'}
+        return cfg_info
 
-        a2, as2, ps2 = _m.notebook_model(g['asimov_angles'])
-        f2 = llh.LnProb(a2, as2, ps2)
-        np.random.seed(25)
-        p0 = mcmc.flat_seed(ps2, 1024)
-        p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
-        # K1: the SM-only log-posterior (161 algorithmic FLOP / 56 B per point) is HBM-bound: report it against HBM
-        n1 = 1 << 24
-        th1 = torch.as_tensor(_m.draw_in_ranges(ps2, 1 << 20, np.random.default_rng(3))).cuda().repeat(16, 1)
-        o1 = torch.empty(n1, dtype=torch.float64, device='cuda')
-        k1 = lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(th1), n1, 6, 1, _lib.ptr(o1), None, None, stream))
-        for _ in range(3):
-            k1()
-        torch.cuda.synchronize()
-        k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        k0e.record()
-        for _ in range(20):
-            k1()
-        k1e.record()
-        torch.cuda.synchronize()
-        k1ms = k0e.elapsed_time(k1e) / 20
-        cfg_info['K1_sm_lnprob'] = {'points': n1, 'ms': k1ms, 'evals_per_s': n1 / (k1ms * 1e-3), 'bound': 'hbm',
-                                    'achieved_gbs': 56.0 * n1 / (k1ms * 1e-3) / 1e9,
-                                    'note': '6-D notebook model (4 PMNS coords + 2 source angles), theta 805 MB > L2'}
-        del th1, o1
-        smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
-        smp.run_mcmc(p0, 200, store=False)
-        sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))
-        cfg_info['C2_emcee_sm_fit'] = {'walkers': 1024, 'steps': 10000, 'ndim': 6, 'seconds': sec, 'evals_per_s': 1024 * 1e4 / sec,
-                                       'acceptance': float(np.mean(smp.acceptance_fraction)), 'launches': 1,
-                                       'note': 'replicas only: every rank runs the same chain shape independently'}
-        # C1: the reference's own CPU-sized case (3 raw source ratios, fixed NuFIT PMNS), here on the device sampler
-        a1, as1, ps1 = _m.sm_fit_c1(g['asimov_angles'])
-        f1 = llh.LnProb(a1, as1, ps1)
-        p1 = mcmc.flat_seed(ps1, 100)
-        smp1 = mcmc.DeviceEnsembleSampler(100, 3, f1, seed=25)
-        smp1.run_mcmc(p1, 100, store=False)
-        sec, _ = timed(lambda: smp1.run_mcmc(None, 1000, store=True, return_tensor=True))
-        cfg_info['C1_sm_fit_fixed_pmns'] = {'walkers': 100, 'steps': 1000, 'ndim': 3, 'seconds': sec, 'evals_per_s': 100 * 1000 / sec,
-                                            'acceptance': float(np.mean(smp1.acceptance_fraction)), 'launches': 1}
-        p3 = mcmc.flat_seed(pset, 4096)
-        smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
-        smp3.run_mcmc(p3, 100, store=False)
-        sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
-        cfg_info['C3_bsm_dim6_fit'] = {'walkers': 4096, 'steps': 2000, 'ndim': fn.ndim, 'seconds': sec, 'evals_per_s': 4096 * 2000 / sec,
-                                       'acceptance': float(np.mean(smp3.acceptance_fraction))}
-        sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first cooperative launches, NCCL float64 path)
-        sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
-        cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
-                                     'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
-                                     'sharding': 'grid points split over %d rank(s), one all-reduce of the summaries' % world}
-        sens.evidence_grid(dimensions=(6,), segments=4, samples=10000)                 # warm-up
-        sec, ev = timed(lambda: sens.evidence_grid(segments=100, samples=1000000))
-        cfg_info['C5_evidence_grid'] = {'grid_points': int(sum(len(v) for v in ev.values())), 'samples_per_point': 1000000, 'seconds': sec,
-                                        'samples_per_s': 6e8 / sec,
-                                        'note': 'Monte-Carlo evidence ln mean(L) per (dimension, scale), what scripts/sens.py gets from MultiNest; '
-                                                'samples sharded over the ranks, two all-reduces of the 600 (max, sum-exp) slots'}
+    try:
+        cfg_info = _configs_section()
+    except Exception as exc:  # noqa: BLE001  (a secondary section must never cost the headline line)
+        cfg_info = {'error': repr(exc)}
 
     if rank == 0:
         base = None
