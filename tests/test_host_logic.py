@@ -438,3 +438,29 @@ def test_harness_cubic_root_seeded_newton_is_full_precision():
     ref = np.array([float(1 - mp.cos(mp.acos(1 - mp.mpf(float(d))) / 3)) for d in delta])
     assert np.max(np.abs(w / ref - 1)) < 2e-13
     assert hh.cubic_w(np.array([0.0]))[0] == 0.0 and np.isnan(hh.cubic_w(np.array([np.nan]))[0])
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on
+    stdout with the contract's keys, timing the oracle port on the host cores; the GPU arm refuses to run
+    without a device instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES='')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['metric'] == 'log-posterior evals/sec' and d['value'] > 10
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
+    gpu = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, env=env, timeout=600)
+    assert gpu.returncode != 0 and 'no CUDA device' in (gpu.stderr + gpu.stdout)
