@@ -306,6 +306,36 @@ def test_theta_memory_layouts_through_the_c_abi(torch, golden):
         assert np.isfinite(ref).mean() > 0.5 and not np.isnan(ref).any()
 
 
+@pytest.mark.parametrize('nbins', [1, 3, 7, 22, 64])
+def test_energy_bin_counts_and_interleave_remainders(torch, golden, nbins):
+    """The energy-bin loop interleaves 2 bins (log-posterior, scans) or 4 (sampler) and finishes the remainder
+    one at a time: every bin count -- one bin, odd counts, counts that are not multiples of four, the maximum
+    of 64 -- against the truth evaluator, and the sampler's stored log-posterior against gf_lnprob."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OUT)
+    args.binning = np.logspace(np.log10(6e4), np.log10(1e7), nbins + 1)
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(40 + nbins)
+    theta = models.draw_in_ranges(pset, 3000, rng)
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    ref = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], model.TEXTURE_ANGLES['OUT'], theta[:, 6], 6, args.binning,
+                                      args.source_ratio)
+    assert np.abs(frs - ref).max() < FR_TOL and not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+    # same model through the scan kernel (texture mode draws its own samples: compare on those)
+    fm = scan.scan_model('texture', dimension=6, texture=Texture.OUT, binning=args.binning)
+    th_s, fr_s, _ = scan.scan_samples(fm, 2000, seed=3)
+    ref_s = truth.eigh_flux_averaged_fr(th_s[:, :4], th_s[:, 4:6], model.TEXTURE_ANGLES['OUT'], th_s[:, 6], 6, args.binning, np.array([1, 2, 0.]) / 3)
+    assert np.abs(fr_s - ref_s).max() < FR_TOL
+    h, kept = scan.scan_histogram(fm, 2000, nb=25, seed=3, distributed=False)
+    assert kept == 2000 and np.array_equal(h, go.ternary_histogram(fr_s, 25))
+    # sampler (four interleaved bins + remainder)
+    np.random.seed(1)
+    p0 = mcmc.flat_seed(pset, 64)
+    smp = mcmc.DeviceEnsembleSampler(64, fn.ndim, fn, seed=3)
+    smp.run_mcmc(p0, 6)
+    assert np.allclose(fn(smp.chain[:, -1]), smp.lnprobability[:, -1], rtol=1e-11, atol=0)
+
+
 def test_bsm_fixed_texture_column_layouts_agree(torch, golden):
     """Same for the fixed-texture BSM model: the scripts/fr.py column layout (4 mixing coordinates, 2 mass
     splittings, logLam) runs with compile-time theta indices, any other layout through the column map --
