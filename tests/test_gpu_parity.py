@@ -306,6 +306,37 @@ def test_theta_memory_layouts_through_the_c_abi(torch, golden):
         assert np.isfinite(ref).mean() > 0.5 and not np.isnan(ref).any()
 
 
+def test_largest_model_sixteen_columns(torch, golden):
+    """GF_MAX_DIM = 16 columns: six SM parameters, five prior-only nuisances, four free new-physics mixing
+    coordinates (Texture.NONE) and logLam -- the generic path at its limit, against the truth evaluator and the
+    oracle's prior; a seventeenth column is refused."""
+    from golemflavor_b200.enums import ParamTag
+    from golemflavor_b200.param import Param, ParamSet
+    g = golden('ref_llh.npz')
+    args, asimov, _ = models.bsm_model_c3(g['asimov_angles'], dim=5, texture=Texture.NONE)
+    p11 = models.bsm11_paramset(5)
+    nuis = [Param(name='nuis%d' % k, value=1.0, ranges=[0., 2.], std=0.3, tag=ParamTag.NUISANCE) for k in range(5)]
+    p16 = ParamSet(list(p11)[:6] + nuis + list(p11)[6:])
+    for k in (6, 7, 8):                                      # Haar-flat NP coordinates inside the unit box
+        p16[11 + k - 6].ranges = [0., 1.]
+    fn = llh.LnProb(args, asimov, p16)
+    assert fn.ndim == 16
+    rng = np.random.default_rng(77)
+    theta = models.draw_in_ranges(p16, 2000, rng)
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    ref_fr = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], theta[:, 11:15], theta[:, 15], 5, models.BINNING, args.source_ratio)
+    assert np.abs(frs - ref_fr).max() < FR_TOL and not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+    lo, hi = np.array(p16.ranges).T
+    kind = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in p16]
+    ref = go.batch_lnprior(theta, lo, hi, kind, list(p16.nominal_values), [p.std or 1.0 for p in p16]) + \
+        go.batch_multi_gaussian(ref_fr, go.angles_to_fr(g['asimov_angles']), 0.02)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lnp), fin) and fin.sum() > 1000
+    assert np.max(np.abs(lnp[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+    with pytest.raises(ValueError):
+        llh.LnProb(args, asimov, ParamSet(list(p16) + [Param(name='one_too_many', value=0., ranges=[-1., 1.], std=1., tag=ParamTag.NUISANCE)]))
+
+
 @pytest.mark.parametrize('nbins', [1, 3, 7, 22, 64])
 def test_energy_bin_counts_and_interleave_remainders(torch, golden, nbins):
     """The energy-bin loop interleaves 2 bins (log-posterior, scans) or 4 (sampler) and finishes the remainder
