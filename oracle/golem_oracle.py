@@ -277,9 +277,19 @@ def flux_averaged_BSMu(theta, args, spectral_index, llh_paramset):
 
     per_bin = []
     for ib in range(len(centers)):
-        u = params_to_BSMu(bsm_angles=bsm_angles, dim=args.dimension,
-                           energy=centers[ib], mass_eigenvalues=mass_eigenvalues,
-                           sm_u=sm_u, no_bsm=args.no_bsm, texture=args.texture)
+        if getattr(args, 'no_bsm', False):
+            # golemflavor/fr.py:437-438: `fr = u_to_fr(source_flux, sm_u)`.  The reference hands the
+            # WHOLE [nbins, 3] flux table to u_to_fr, whose einsum 'ai,bi,a->b' rejects a 2-D source:
+            # the unmodified reference raises ValueError on this branch for every binning (checked in
+            # the build container, tests/golden/make_golden.py docstring).  The evident intent -- no
+            # new physics, vacuum mixing with sm_u in every energy bin -- is restated per bin and sent
+            # through the same width-weighted average; E^gamma cancels in u_to_fr's normalisation, so
+            # the result is u_to_fr(args.source_ratio, sm_u) whatever the binning.
+            u = np.array(sm_u, dtype=CLD)
+        else:
+            u = params_to_BSMu(bsm_angles=bsm_angles, dim=args.dimension,
+                               energy=centers[ib], mass_eigenvalues=mass_eigenvalues,
+                               sm_u=sm_u, no_bsm=args.no_bsm, texture=args.texture)
         per_bin.append(u_to_fr(source_flux[ib], u))
     measured = np.array(per_bin).T
     integrated = np.sum(measured * widths, axis=1)
@@ -329,6 +339,25 @@ def lnprior(theta, paramset):
     return total
 
 
+def source_from_params(src, args):
+    """Source composition from the SRCANGLES-tagged values of a parameter set:
+    two values are the angles (sin^4 phi, cos 2psi) of ``angles_to_fr``
+    (golemflavor/llh.py:104-110, examples/inference.ipynb cell 21); one value is
+    x with source (x, 1-x, 0) (scripts/mc_x.py:187); three values are raw
+    flavor ratios, normalised later by ``u_to_fr`` (golemflavor/fr.py:535 --
+    BASELINE config 1, "3 source-flavor params, fixed PMNS"); none:
+    ``args.source_ratio``."""
+    if len(src) == 2:
+        return angles_to_fr(src)
+    if len(src) == 1:
+        return (src[0], 1.0 - src[0], 0.0)
+    if len(src) == 3:
+        return tuple(src)
+    if src:
+        raise ValueError('expected one, two or three SRCANGLES params, got {0}'.format(len(src)))
+    return args.source_ratio
+
+
 def triangle_llh_gauss(theta, args, asimov_paramset, llh_paramset):
     """Gaussian flavor-ratio likelihood composed as in the reference notebooks
     (examples/inference.ipynb cell 21, examples/tutorial.ipynb), generalised to
@@ -354,18 +383,18 @@ def triangle_llh_gauss(theta, args, asimov_paramset, llh_paramset):
 
     src = [p.value for p in params if _tagname(p.tag) == 'SRCANGLES']
     has_scale = any(_tagname(p.tag) == 'SCALE' for p in params)
+    source = source_from_params(src, args)
     if has_scale:
         gamma = getattr(args, 'spectral_index', -2.0)
         if src:
             args = deepcopy(args)
-            args.source_ratio = np.array(angles_to_fr(src))
+            args.source_ratio = np.array(source)
         fr = flux_averaged_BSMu(theta, args, gamma, llh_paramset)
     else:
         names = ['s_12_2', 'c_13_4', 's_23_2', 'dcp']
         sm = [p.value for p in params if _tagname(p.tag) == 'SM_ANGLES'
               and p.name in names]
         sm_u = angles_to_u(sm) if len(sm) == 4 else NUFIT_U
-        source = angles_to_fr(src) if src else args.source_ratio
         fr = u_to_fr(source, sm_u)
     return multi_gaussian(fr, fr_bf, smearing)
 

@@ -76,3 +76,34 @@ def sm_fit_c1(asimov_angles, smearing=0.02):
     eps = 1e-6
     src = [Param(name='f_%s' % n, value=1. / 3, ranges=[eps, 1.], tag=tag) for n in ('e', 'mu', 'tau')]
     return Namespace(source_ratio=[1, 2, 0], no_bsm=True), asimov, ParamSet(src)
+
+
+SOURCE_KINDS = {'angles': 2, 'x': 1, 'ratios': 3}
+
+
+def source_params(kind):
+    """SRCANGLES-tagged source parametrisations the reference composes (llh.py:104-110: two angles;
+    scripts/mc_x.py:187: x -> (x, 1-x, 0); BASELINE config 1: three raw ratios normalised by u_to_fr)."""
+    tag = ParamTag.SRCANGLES
+    if kind == 'angles':
+        return [Param(name='astroFlavorAngle1', value=0.5, ranges=[0., 1.], tag=tag),
+                Param(name='astroFlavorAngle2', value=0., ranges=[-1., 1.], tag=tag)]
+    if kind == 'x':
+        return [Param(name='astroX', value=0.5, seed=[0., 1.], ranges=[0., 1.], std=0.1, tag=tag)]
+    if kind == 'ratios':
+        return [Param(name='f_%s' % n, value=1. / 3, ranges=[1e-6, 1.], tag=tag) for n in ('e', 'mu', 'tau')]
+    raise ValueError(kind)
+
+
+def bsm_sampled_source(asimov_angles, kind='angles', dim=6, texture=Texture.OET, smearing=0.02, source_first=False):
+    """The composition of llh.py:94-112 with a SAMPLED source on the binned BSM path: 6 SM params +
+    the source parameters + logLam (source columns optionally ahead of the SM block: the column map is
+    a runtime property of the model)."""
+    tag = ParamTag.BESTFIT
+    asimov = ParamSet([
+        Param(name='measured_angle1', value=float(asimov_angles[0]), ranges=[0., 1.], std=smearing, tag=tag),
+        Param(name='measured_angle2', value=float(asimov_angles[1]), ranges=[-1., 1.], std=smearing, tag=tag)])
+    b = SCALE_BOUNDARIES[dim]
+    scale = [Param(name='logLam', value=float(np.mean(b)), ranges=list(b), std=3, tag=ParamTag.SCALE)]
+    sm, src = sm_paramset(with_mass=True), source_params(kind)
+    return bsm_args(dim, texture), asimov, ParamSet((src + sm if source_first else sm + src) + scale)

@@ -474,6 +474,171 @@ def test_bsm_lnprob_against_oracle(torch, golden, texture, dim):
     assert np.all(np.abs(lnp[fin] - ref[fin]) <= tol)
 
 
+def _prior_tables(pset):
+    lo, hi = np.array(pset.ranges).T
+    kind = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in pset]
+    return lo, hi, kind, list(pset.nominal_values), [p.std or 1.0 for p in pset]
+
+
+def _source_of(kind, cols):
+    if kind == 'angles':
+        return go.batch_angles_to_fr(cols)
+    if kind == 'x':
+        return np.column_stack([cols[:, 0], 1.0 - cols[:, 0], np.zeros(len(cols))])
+    return cols
+
+
+def test_golden_config1_and_sampled_source_models(torch, golden):
+    """BASELINE config 1 (three raw source ratios, PMNS fixed at NUFIT_U: `col_src3`, SM specialisation) and the
+    sampled-source compositions of llh.py:94-112 on the binned BSM path (GENERIC specialisation), through
+    gf_lnprob and gf_flux_averaged_fr, against fixtures from the unmodified reference (make_golden_r2.py)."""
+    g, gl = golden('ref_src.npz'), golden('ref_llh.npz')
+    args, asimov, pset = models.sm_fit_c1(gl['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    assert list(fn.model.struct.col_src3) == [0, 1, 2] and fn.model.struct.no_bsm == 1
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(g['c1_theta'], want_fr=True, want_status=True))
+    fin = np.isfinite(g['c1_lnprob'])
+    inside = np.all((g['c1_theta'] >= 1e-6) & (g['c1_theta'] <= 1), axis=1)
+    assert np.array_equal(np.isfinite(lnp), fin) and np.all(st[~inside] & _lib.ST_OUT_OF_PRIOR) and np.all(st[inside] == 0)
+    assert np.abs(frs[inside] - g['c1_fr'][inside]).max() < 1e-14
+    assert np.max(np.abs(lnp[fin] - g['c1_lnprob'][fin]) / np.abs(g['c1_lnprob'][fin])) < LLH_RTOL
+    # the reference signature (scalar theta) and the flux-averaged entry point on the no-BSM branch (fr.py:437-438)
+    assert abs(llh.ln_prob(list(g['c1_theta'][0]), args, asimov, pset) - g['c1_lnprob'][0]) < LLH_RTOL * abs(g['c1_lnprob'][0])
+    a2 = argparse.Namespace(source_ratio=[1, 2, 0], no_bsm=True, binning=g['binning'], dimension=6, texture=Texture.OET)
+    assert np.abs(fr.flux_averaged_BSMu(g['c1_theta'][inside], a2, -2.0, pset) - g['c1_fr'][inside]).max() < 1e-14
+    for kind in ('angles', 'x', 'ratios'):
+        nsrc = models.SOURCE_KINDS[kind]
+        for tex, dim in (('OET', 6), ('OUT', 6), ('OEU', 3), ('OET', 8)):
+            sel = (g['sb_kind'] == kind) & (g['sb_tex'] == tex) & (g['sb_dim'] == dim)
+            theta = np.column_stack([g['sb_sm'][sel], g['sb_src'][sel][:, :nsrc], g['sb_loglam'][sel]])
+            for first in (False, True):
+                args, asimov, ps = models.bsm_sampled_source(gl['asimov_angles'], kind, dim, Texture[tex], source_first=first)
+                th = np.column_stack([theta[:, 6:6 + nsrc], theta[:, :6], theta[:, -1:]]) if first else theta
+                fn = llh.LnProb(args, asimov, ps)
+                lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(th, want_fr=True, want_status=True))
+                assert not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY | _lib.ST_OUT_OF_PRIOR))
+                assert np.abs(frs - g['sb_fr'][sel]).max() < FR_TOL, (kind, tex, dim)
+                assert np.abs(fr.flux_averaged_BSMu(th, args, -2.0, ps) - frs).max() == 0.0
+                ref = go.batch_lnprior(th, *_prior_tables(ps)) + g['sb_llh'][sel]
+                ok = np.isfinite(ref)
+                assert np.array_equal(np.isfinite(lnp), ok)
+                d = np.linalg.norm(g['sb_fr'][sel][ok] - g['bf'], axis=1)
+                assert np.all(np.abs(lnp[ok] - ref[ok]) <= np.maximum(LLH_RTOL * np.abs(ref[ok]), 2e-10 * d / 0.02 ** 2))
+
+
+@pytest.mark.parametrize('kind', ['angles', 'x', 'ratios'])
+def test_sampled_source_bsm_lnprob_against_oracle(torch, golden, kind):
+    """GF_SPEC_GENERIC with a sampled source AND a SCALE column (gf_model.cuh: per-point 1 / (S wsum)
+    normalisation, one bin chain in the scans, two in k_lnprob) on 20 000 points per texture against the
+    oracle: LAPACK-truth compositions + batch lnprior + batch multi_gaussian."""
+    g = golden('ref_llh.npz')
+    bf = np.array(go.angles_to_fr(g['asimov_angles']))
+    nsrc = models.SOURCE_KINDS[kind]
+    for tex, dim in (('OET', 6), ('OUT', 4)):
+        rng = np.random.default_rng(31 + dim)
+        n = 20000
+        args, asimov, pset = models.bsm_sampled_source(g['asimov_angles'], kind, dim, Texture[tex])
+        theta = models.draw_in_ranges(pset, n, rng, seeds=False)
+        theta[:, :6] = models.draw_in_ranges(models.bsm7_paramset(dim), n, rng, seeds=True)[:, :6]
+        theta[::89, 6] = 1.5                                   # source parameter outside its box
+        fn = llh.LnProb(args, asimov, pset)
+        assert fn.model.struct.col_scale == 6 + nsrc and fn.model.struct.no_bsm == 0
+        lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+        lp = go.batch_lnprior(theta, *_prior_tables(pset))
+        inside = np.isfinite(lp)
+        ti = theta[inside]
+        src = _source_of(kind, ti[:, 6:6 + nsrc])
+        ref_fr = truth.eigh_flux_averaged_fr(ti[:, :4], ti[:, 4:6], np.broadcast_to(model.TEXTURE_ANGLES[tex], (len(ti), 4)),
+                                             ti[:, -1], dim, models.BINNING, src)
+        assert np.all(np.isneginf(lnp[~inside])) and np.all(st[~inside] & _lib.ST_OUT_OF_PRIOR)
+        assert not np.any(st[inside] & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY | _lib.ST_OUT_OF_PRIOR))
+        assert np.abs(frs[inside] - ref_fr).max() < FR_TOL
+        with np.errstate(invalid='ignore'):
+            ref = lp[inside] + go.batch_multi_gaussian(ref_fr, bf, 0.02)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(lnp[inside]), fin)
+        d = np.linalg.norm(ref_fr[fin] - bf, axis=1)
+        assert np.all(np.abs(lnp[inside][fin] - ref[fin]) <= np.maximum(LLH_RTOL * np.abs(ref[fin]), 2e-11 * d / 0.02 ** 2))
+        # the same model through the scan kernels (ILP 1 instantiation of the generic bin loop): draws + compositions
+        fm = model.flatten(args, None, pset, likelihood='FLAT')
+        th_s, fr_s, st_s = scan.scan_samples(fm, 4000, seed=7)
+        src_s = _source_of(kind, th_s[:, 6:6 + nsrc])
+        ref_s = truth.eigh_flux_averaged_fr(th_s[:, :4], th_s[:, 4:6], np.broadcast_to(model.TEXTURE_ANGLES[tex], (4000, 4)),
+                                            th_s[:, -1], dim, models.BINNING, src_s)
+        assert np.abs(fr_s - ref_s).max() < FR_TOL and not np.any(st_s & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY))
+        h, kept = scan.scan_histogram(fm, 4000, nb=25, seed=7, distributed=False)
+        assert kept == 4000 and np.array_equal(h, go.ternary_histogram(fr_s, 25))
+
+
+def test_config1_lnprob_and_sampler_against_oracle(torch, golden):
+    """BASELINE config 1 at scale and inside the device-resident sampler (`col_src3` on the SM specialisation):
+    20 000 points against the oracle's u_to_fr(theta, NUFIT_U) + multi_gaussian; the sampler's chain is replayed by
+    the NumPy stretch move scoring proposals with the ORACLE (longdouble) log-posterior."""
+    import ref_sampler
+    g = golden('ref_llh.npz')
+    bf = np.array(go.angles_to_fr(g['asimov_angles']))
+    args, asimov, pset = models.sm_fit_c1(g['asimov_angles'])
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(41)
+    theta = rng.uniform(1e-6, 1.0, (20000, 3))
+    theta[::53, 2] = 1.2
+    lnp, frs, st = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    inside = np.all((theta >= 1e-6) & (theta <= 1), axis=1)
+    ref_fr = go.batch_u_to_fr(theta[inside], np.broadcast_to(go.NUFIT_U, (inside.sum(), 3, 3))).astype(np.float64)
+    assert np.all(np.isneginf(lnp[~inside])) and np.abs(frs[inside] - ref_fr).max() < 1e-14
+    ref = go.batch_multi_gaussian(ref_fr, bf, 0.02)
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(lnp[inside]), fin)
+    assert np.max(np.abs(lnp[inside][fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+
+    def oracle_lnprob(q):
+        q = np.atleast_2d(q)
+        ok = np.all((q >= 1e-6) & (q <= 1), axis=1)
+        out = np.full(len(q), -np.inf)
+        if ok.any():
+            f = go.batch_u_to_fr(q[ok], np.broadcast_to(go.NUFIT_U, (ok.sum(), 3, 3))).astype(np.float64)
+            out[ok] = go.batch_multi_gaussian(f, bf, 0.02)
+        return out
+
+    k = 100                                             # BASELINE config 1: 100 walkers
+    p0 = np.array([1.0, 0.0, 0.0]) * rng.uniform(0.5, 0.9, (k, 1)) + rng.uniform(1e-3, 0.05, (k, 3))
+    l0 = fn(p0)
+    assert np.all(np.isfinite(l0)) and np.max(np.abs(l0 - oracle_lnprob(p0)) / np.abs(l0)) < LLH_RTOL
+    chains = []
+    for mode in (0, 1, 2, 3):
+        s = mcmc.DeviceEnsembleSampler(k, 3, fn, seed=9, mode=mode)
+        s.run_mcmc(p0, 200)
+        chains.append((s.chain, s.lnprobability))
+        assert np.array_equal(s.chain, chains[0][0]) and np.array_equal(s.lnprobability, chains[0][1]), mode
+    _, _, rchain, racc = ref_sampler.run(oracle_lnprob, p0, oracle_lnprob(p0), 200, seed=9)
+    # identical unless an acceptance test falls within the ~1e-13 difference between the fp64 kernel and the oracle
+    assert np.mean(chains[0][0] == rchain) > 0.99
+    assert 0.2 < np.mean(racc) / 200 < 0.8
+
+
+def test_device_sampler_sampled_source_bsm_model(torch, golden):
+    """SRCANGLES + SCALE inside the sampler (GENERIC specialisation, ILP 2): all launch shapes give the same chain, the
+    stored log-posteriors are gf_lnprob's for the stored positions, and the chain replays under the NumPy stretch move."""
+    import ref_sampler
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_sampled_source(g['asimov_angles'], 'angles', 6, Texture.OET)
+    fn = llh.LnProb(args, asimov, pset)
+    rng = np.random.default_rng(17)
+    k = 128
+    p0 = models.draw_in_ranges(models.bsm7_paramset(6), k, rng, seeds=True)
+    p0 = np.column_stack([p0[:, :6], rng.uniform(0.8, 1.0, k), rng.uniform(0.6, 1.0, k), rng.uniform(-50, -35, k)])
+    ref = mcmc.DeviceEnsembleSampler(k, fn.ndim, fn, seed=21, mode=1)
+    ref.run_mcmc(p0, 25)
+    for mode, nc in ((0, 0), (2, 0), (3, 2)):
+        s = mcmc.DeviceEnsembleSampler(k, fn.ndim, fn, seed=21, mode=mode, cluster_blocks=nc)
+        s.run_mcmc(p0, 25)
+        assert np.array_equal(s.chain, ref.chain) and np.array_equal(s.lnprobability, ref.lnprobability), (mode, nc)
+    assert np.allclose(fn(ref.chain[:, -1]), ref.lnprobability[:, -1], rtol=1e-11, atol=0)
+    _, _, rchain, _ = ref_sampler.run(lambda q: fn(q), p0, fn(p0), 25, seed=21)
+    assert np.mean(ref.chain == rchain) > 0.99
+    assert 0.02 < ref.acceptance_fraction.mean() < 0.9
+
+
 def test_anarchic_free_np_angles_against_oracle(torch):
     rng = np.random.default_rng(9)
     n = 20000

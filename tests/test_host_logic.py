@@ -415,6 +415,55 @@ def test_harness_config1_three_source_ratios_fixed_pmns(golden):
     assert np.abs(hh.lnprob(fm, theta * 0.5)[1] - fr).max() < 1e-15
 
 
+def _sampled_source_cases(g):
+    """(kind, texture, dim, theta rows in the product's column order, reference fr, reference llh) per group of ref_src.npz."""
+    for kind in ('angles', 'x', 'ratios'):
+        nsrc = models.SOURCE_KINDS[kind]
+        for tex, dim in (('OET', 6), ('OUT', 6), ('OEU', 3), ('OET', 8)):
+            sel = (g['sb_kind'] == kind) & (g['sb_tex'] == tex) & (g['sb_dim'] == dim)
+            theta = np.column_stack([g['sb_sm'][sel], g['sb_src'][sel][:, :nsrc], g['sb_loglam'][sel]])
+            yield kind, tex, dim, theta, g['sb_fr'][sel], g['sb_llh'][sel]
+
+
+def test_harness_sampled_source_models_match_reference_fixture(golden):
+    """The GENERIC specialisation with a sampled source (two angles / x / three raw ratios) on the binned
+    BSM path and BASELINE config 1, against fixtures from the unmodified reference (make_golden_r2.py)."""
+    g, gl = golden('ref_src.npz'), golden('ref_llh.npz')
+    args, asimov, pset = models.sm_fit_c1(gl['asimov_angles'])
+    lnp, fr, st = hh.lnprob(model.flatten(args, asimov, pset), g['c1_theta'])
+    fin = np.isfinite(g['c1_lnprob'])
+    assert np.array_equal(np.isfinite(lnp), fin)
+    assert np.abs(fr[fin] - g['c1_fr'][fin]).max() < 1e-14
+    assert np.max(np.abs(lnp[fin] - g['c1_lnprob'][fin]) / np.abs(g['c1_lnprob'][fin])) < 1e-10
+    for kind, tex, dim, theta, ref_fr, ref_llh in _sampled_source_cases(g):
+        for first in (False, True):
+            args, asimov, ps = models.bsm_sampled_source(gl['asimov_angles'], kind, dim, Texture[tex], source_first=first)
+            fm = model.flatten(args, asimov, ps)
+            assert model_spec_name(fm) == 'GENERIC'
+            nsrc = models.SOURCE_KINDS[kind]
+            th = np.column_stack([theta[:, 6:6 + nsrc], theta[:, :6], theta[:, -1:]]) if first else theta
+            lnp, fr, st = hh.lnprob(fm, th)
+            assert not np.any(st & (_lib.ST_NON_FINITE | _lib.ST_NON_UNITARY | _lib.ST_OUT_OF_PRIOR))
+            # the reference's float128 Cardano is itself only good to ~1e-11 on part of these points (SURVEY 7.1)
+            assert np.abs(fr - ref_fr).max() < 1e-10, (kind, tex, dim)
+            lo, hi = np.array(ps.ranges).T
+            kinds = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in ps]
+            lp = go.batch_lnprior(th, lo, hi, kinds, list(ps.nominal_values), [p.std or 1.0 for p in ps])
+            ref = lp + ref_llh
+            fin = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(lnp), fin)
+            d = np.linalg.norm(ref_fr[fin] - g['bf'], axis=1)
+            assert np.all(np.abs(lnp[fin] - ref[fin]) <= np.maximum(1e-10 * np.abs(ref[fin]), 2e-10 * d / 0.02 ** 2))
+
+
+def model_spec_name(fm):
+    s = fm.struct
+    fixed_source = s.col_src[0] < 0 and s.col_x < 0 and s.col_src3[0] < 0
+    if s.no_bsm:
+        return 'SM'
+    return 'GENERIC' if not fixed_source else 'NPFREE' if any(c >= 0 for c in s.col_np) else 'FIXED'
+
+
 def test_cli_identifiers_match_reference_naming():
     from argparse import Namespace
     from golemflavor_b200 import cli

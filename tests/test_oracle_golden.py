@@ -284,3 +284,64 @@ def test_ternary_histogram_definition():
     h = go.ternary_histogram(frs, 25)
     assert h.shape == (26, 26, 26) and h.sum() == 5000
     assert h[25, 0, 0] >= 1        # x == 1.0 lands in the last bin (np.histogramdd)
+
+
+# ---------------------------------------------------------------- sampled-source models (round 2)
+def _asimov(bf):
+    ang = go.fr_to_angles(bf)
+    return [_P('measured_angle1', float(ang[0]), (0., 1.), None, 0.02, 'BESTFIT'), _P('measured_angle2', float(ang[1]), (-1., 1.), None, 0.02, 'BESTFIT')]
+
+
+def test_golden_config1_three_source_ratios(golden):
+    """BASELINE config 1 -- three raw source ratios, PMNS fixed at NUFIT_U -- against the unmodified
+    reference (tests/golden/make_golden_r2.py: lnprior + multi_gaussian(u_to_fr(theta, NUFIT_U)))."""
+    g = golden('ref_src.npz')
+    pset = [_P('f_%s' % n, 1. / 3, (1e-6, 1.), None, None, 'SRCANGLES') for n in ('e', 'mu', 'tau')]
+    args = argparse.Namespace(source_ratio=[1, 2, 0], no_bsm=True)
+    asimov = _asimov(g['bf'])
+    with np.errstate(divide='ignore'):
+        got = np.array([go.ln_prob(list(t), args, asimov, pset) for t in g['c1_theta']], dtype=np.float64)
+    ref = g['c1_lnprob']
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and fin.sum() > 150
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) < 1e-12
+
+
+def test_golden_sampled_source_on_the_bsm_path(golden):
+    """llh.py:94-112 composition (flux_averaged_BSMu with the source taken from the SRCANGLES values,
+    multi_gaussian for GolemFit) for the three source parametrisations, against the reference."""
+    g = golden('ref_src.npz')
+    asimov = _asimov(g['bf'])
+    worst_fr, worst_llh = 0.0, 0.0
+    for i in range(len(g['sb_kind'])):
+        kind, tex, dim = str(g['sb_kind'][i]), str(g['sb_tex'][i]), int(g['sb_dim'][i])
+        nsrc = {'angles': 2, 'x': 1, 'ratios': 3}[kind]
+        pset = _bsm_pset(dim, go.TEXTURE_ANGLES[tex])
+        pset = pset[:6] + [_P('src%d' % k, 0.5, (-1., 1.), None, None, 'SRCANGLES') for k in range(nsrc)] + pset[6:]
+        theta = list(g['sb_sm'][i]) + list(g['sb_src'][i][:nsrc]) + list(go.TEXTURE_ANGLES[tex]) + [float(g['sb_loglam'][i])]
+        args = argparse.Namespace(binning=g['binning'], source_ratio=[1, 2, 0], dimension=dim, texture='NONE', no_bsm=False)
+        src = go.source_from_params(list(g['sb_src'][i][:nsrc]), args)
+        a2 = argparse.Namespace(**vars(args))
+        a2.source_ratio = np.array(src, dtype=np.float64)
+        fr = np.asarray(go.flux_averaged_BSMu(theta, a2, -2.0, pset), dtype=np.float64)
+        worst_fr = max(worst_fr, np.abs(fr - g['sb_fr'][i]).max())
+        with np.errstate(divide='ignore'):
+            llh = float(go.triangle_llh_gauss(theta, args, asimov, pset))
+        if np.isfinite(g['sb_llh'][i]):
+            worst_llh = max(worst_llh, abs(llh - g['sb_llh'][i]) / abs(g['sb_llh'][i]))
+        else:
+            assert llh == g['sb_llh'][i]
+    assert worst_fr < 1e-13 and worst_llh < 1e-11, (worst_fr, worst_llh)
+
+
+def test_no_bsm_branch_of_flux_averaged(golden):
+    """fr.py:437-438: the reference raises on this branch (recorded in the fixture); the oracle restates
+    the intent, u_to_fr(source_ratio, sm_u), independent of the binning."""
+    g = golden('ref_src.npz')
+    assert all(str(r) == 'ValueError' for r in g['nb_raised'])
+    pset = [_P('logLam', -40., (-56, -30), None, 3, 'SCALE')]
+    for s, ref in zip(g['nb_src'], g['nb_fr']):
+        for binning in (g['binning'], g['binning'][:2], g['binning'][::5]):
+            args = argparse.Namespace(binning=binning, source_ratio=s / s.sum(), dimension=6, texture='NONE', no_bsm=True)
+            got = np.asarray(go.flux_averaged_BSMu([-40.], args, -2.0, pset), dtype=np.float64)
+            assert np.abs(got - ref).max() < 1e-15
