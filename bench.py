@@ -14,15 +14,23 @@ the hot path over that batch = ONE kernel launch.
              launching stream, barrier + synchronize on both sides, max over ranks)
   e2e      : same metric through the public host API (`llh.LnProb.evaluate_host` -> C ABI
              `gf_lnprob_host`): pinned host theta -> chunked H2D -> kernel -> D2H of the results
-  roofline : algorithmic fp64 FLOPs (9252 per evaluation) / kernel time, against the
-             fp64 FMA peak MEASURED in the same run by a DFMA microbenchmark (MEASURED_PEAKS.json
-             carries no fp64 figure); HBM traffic is reported alongside
-  scan     : secondary section -- the sharded Monte-Carlo scan (config 4), whole-job samples / s
-             including the NCCL all-reduce of the histograms
-  cpu_baseline : the oracle's scalar float128 ln_prob (port of the reference path) on 1 host core
+  roofline : EXECUTED fp64 instructions of the kernel (per point: counted by ncu for this very build,
+             profiles/roofline_traffic.json, "ncu, offline") x evaluations / kernel time, as FMA-issue
+             equivalents (2 FLOP per issue slot), against the fp64 FMA peak MEASURED in the same run by a
+             DFMA microbenchmark (MEASURED_PEAKS.json carries no fp64 figure): `frac` is the share of
+             the fp64 pipe's issue slots the kernel uses, <= 1 by construction.  The throughput in
+             ALGORITHMIC FLOPs (9252 per evaluation of the reference's formulas; the
+             kernel's own algebra needs fewer) is reported beside it as `algorithmic_tflops` /
+             `algorithmic_ratio`; `sustained_*` repeats the measurement over >= 1 s of launches
+  config   : besides the workload, the secondary sections the driver must keep: the sharded
+             Monte-Carlo scan (config 4, `scan_*`: whole-job seconds incl. the NCCL all-reduce of the
+             histograms, checksum) and the sampler-shaped configs C1/C2/C3/C5 and K1 (`c*_`, `k1_*`)
+  cpu_baseline : the oracle's scalar float128 ln_prob (port of the reference path) on 1 host core for
+             the headline model, plus the config-2 notebook model and config 1 end to end on the CPU
 
 `--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure
-Python and cannot travel to the GPU box) on all host cores for the same metric and config.
+Python and cannot travel to the GPU box) on all host cores for the same metric and config: exactly
+K steps after W warm-up steps, each step a bounded sample of the workload.
 """
 
 import argparse
@@ -113,12 +121,23 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
+_CPU_STATE = {}
+
+
+def _cpu_problem():
+    """Model + oracle of the headline workload, built once per process (fork pool workers inherit it)."""
+    if 'problem' not in _CPU_STATE:
+        import models  # noqa: F401  (sys.path set at import)
+        from oracle import golem_oracle as go
+        (args, asimov, pset), _ = build_problem()
+        _CPU_STATE['problem'] = (go, args, asimov, pset)
+    return _CPU_STATE['problem']
+
+
 def _cpu_eval_chunk(job):
     """Scalar float128 ln_prob of the oracle (restatement of llh.py:121-130 + fr.py) on a chunk."""
     seed, count = job
-    import models  # noqa: F401  (sys.path set at import)
-    from oracle import golem_oracle as go
-    (args, asimov, pset), _ = build_problem()
+    go, args, asimov, pset = _cpu_problem()
     theta = synth_theta(pset, count, seed, sys.modules['models'])
     t0 = time.perf_counter()
     out = []
@@ -130,42 +149,94 @@ def _cpu_eval_chunk(job):
     return time.perf_counter() - t0, count, float(np.sum(np.isfinite(out)))
 
 
-def cpu_baseline(per_core, cores):
-    jobs = [(1000 + c, per_core) for c in range(cores)]
+def cpu_baseline(per_core, cores, pool=None, seed0=1000):
+    jobs = [(seed0 + c, per_core) for c in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
         res = [_cpu_eval_chunk(jobs[0])]
+    elif pool is not None:
+        res = pool.map(_cpu_eval_chunk, jobs, chunksize=1)
     else:
         import multiprocessing as mp
-        with mp.get_context('fork').Pool(cores) as pool:
-            res = pool.map(_cpu_eval_chunk, jobs)
+        with mp.get_context('fork').Pool(cores) as p:
+            res = p.map(_cpu_eval_chunk, jobs, chunksize=1)
     wall = time.perf_counter() - t0
     total = sum(r[1] for r in res)
     compute = max(r[0] for r in res)
     return total / compute, total, wall
 
 
+def cpu_baseline_c2(count):
+    """Config-2 model (examples/inference.ipynb:307-366: 4 PMNS coordinates with LIMITEDGAUSS priors + 2 source
+    angles, Gaussian LLH): the oracle's scalar float128 ln_prob on one core (~252 evals/s/core
+    for the unmodified reference)."""
+    import models as _m
+    from oracle import golem_oracle as go
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+    args, asimov, pset = _m.notebook_model(g['asimov_angles'])
+    theta = _m.draw_in_ranges(pset, count, np.random.default_rng(25), seeds=True)
+    t0 = time.perf_counter()
+    with np.errstate(divide='ignore'):
+        for t in theta:
+            go.ln_prob(list(t), args, asimov, pset)
+    sec = time.perf_counter() - t0
+    return {'value': count / sec, 'unit': 'evals/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d scalar float128 ln_prob evaluations of the 6-D notebook model (%.1f s)' % (count, sec)}
+
+
+def cpu_baseline_c1(nsteps):
+    """Config 1 END TO END on the CPU: 100 walkers, 3 raw source ratios, PMNS fixed at NUFIT_U,
+    the bundled NumPy stretch-move sampler (emcee is absent) scoring one walker per call with the oracle's scalar
+    ln_prob, like emcee-2 with threads=1.  A bounded number of steps of the 1000-step chain."""
+    import models as _m
+    from golemflavor_b200 import mcmc
+    from oracle import golem_oracle as go
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+    args, asimov, pset = _m.sm_fit_c1(g['asimov_angles'])
+    np.random.seed(25)
+    p0 = mcmc.flat_seed(pset, 100)
+
+    def lnp(t):
+        with np.errstate(divide='ignore'):
+            v = go.ln_prob(list(t), args, asimov, pset)
+        return v if v == v else -np.inf
+
+    smp = mcmc.EnsembleSampler(100, 3, lnp, vectorize=False, seed=25)
+    t0 = time.perf_counter()
+    smp.run_mcmc(p0, nsteps)
+    sec = time.perf_counter() - t0
+    evals = 100 * (nsteps + 1)
+    return {'value': evals / sec, 'unit': 'evals/s', 'cores': 1, 'kind': 'port', 'seconds_per_1000_steps': sec * 1000.0 / nsteps,
+            'sample': '%d of the 1000 steps of the 100-walker chain, end to end on 1 core (%.1f s)' % (nsteps, sec)}
+
+
 def run_reference(opts):
+    """The reference arm: the oracle port on all host cores (emcee-2 `threads=N` style fork pool), EXACTLY K timed
+    steps after W warm-up steps; a step is a bounded sample of the workload (the same synthetic theta distribution)
+    sized so that the whole run takes about half a minute whatever K and W are."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_core = 150
-    for _ in range(max(0, min(opts.warmup, 1))):
-        cpu_baseline(8, cores)
-    vals = []
-    t0 = time.perf_counter()
-    steps = max(1, min(opts.steps, 3))
-    for _ in range(steps):
-        v, total, _ = cpu_baseline(per_core, cores)
-        vals.append(v)
-    elapsed = time.perf_counter() - t0
-    value = float(np.mean(vals))
+    steps, warmup = max(1, opts.steps), max(0, opts.warmup)
+    per_core = int(min(150, max(4, round(30.0 * 90.0 / (steps + warmup)))))   # ~90 evals/s/core
+    _cpu_problem()
+    with mp.get_context('fork').Pool(cores) as pool:
+        for w in range(warmup):
+            cpu_baseline(per_core, cores, pool, seed0=500000 + 1000 * w)
+        t0 = time.perf_counter()
+        total = 0
+        for k in range(steps):
+            _, n, _ = cpu_baseline(per_core, cores, pool, seed0=1000 * (k + 1))
+            total += n
+        elapsed = time.perf_counter() - t0
+    value = total / elapsed
     sample = '{0} scalar float128 ln_prob evaluations per step ({1} per process x {2} processes), same model and synthetic theta ' \
              'distribution as the GPU arm'.format(per_core * cores, per_core, cores)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': opts.gpus, 'steps': steps,
-        'warmup': min(opts.warmup, 1), 'ms_per_step': 1e3 * elapsed / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': warmup, 'ms_per_step': 1e3 * elapsed / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f80 (x87 long double, as the reference)', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'sample': sample},
         'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
@@ -176,7 +247,15 @@ def run_reference(opts):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def _note(*a):
+    """Details that do not belong into the one JSON line go to stderr."""
+    sys.stderr.write(' '.join(str(x) for x in a) + '\n')
+    sys.stderr.flush()
+
+
 def run_gpu(opts):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
     from golemflavor_b200 import _lib, llh, scan
@@ -187,12 +266,18 @@ def run_gpu(opts):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
+    numa = None
     try:  # keep this rank (and the pinned buffers it first-touches) on the CPUs / NUMA node next to its GPU
         import pynvml
         pynvml.nvmlInit()
         visible = os.environ.get('CUDA_VISIBLE_DEVICES')
         phys = int(visible.split(',')[local]) if visible and visible.split(',')[local].isdigit() else local
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        try:
+            numa = int(pynvml.nvmlDeviceGetNumaNodeId(handle))
+        except Exception:  # noqa: BLE001
+            numa = None
     except Exception:  # noqa: BLE001  (affinity is an optimisation, never a requirement)
         pass
     if world > 1:
@@ -204,12 +289,18 @@ def run_gpu(opts):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x):
+    def over_ranks(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
+
+    def max_over_ranks(x):
+        return over_ranks(x, dist.ReduceOp.MAX)
+
+    def min_over_ranks(x):
+        return over_ranks(x, dist.ReduceOp.MIN)
 
     (args, asimov, pset), models = build_problem()
     fn = llh.LnProb(args, asimov, pset)
@@ -224,7 +315,6 @@ def run_gpu(opts):
 
     # -- fp64 peak probe (same run, same clocks)
     sink = torch.zeros(8, dtype=torch.float64, device='cuda')
-    import ctypes as C
     flops = C.c_double()
     peak = 0.0
     for _ in range(4):
@@ -235,7 +325,7 @@ def run_gpu(opts):
         torch.cuda.synchronize()
         peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 
-    # -- device-resident throughput
+    # -- device-resident throughput: exactly K steps
     for _ in range(opts.warmup):
         step()
     clocks = ClockSampler(local)
@@ -256,6 +346,25 @@ def run_gpu(opts):
     value = world * n * opts.steps / (ms * 1e-3)
     kernel_ms = ms / opts.steps
 
+    # -- the same launch repeated for >= 1 s (the K-step region is a burst of a few ms): sustained clocks and rate
+    sus_steps = int(max(opts.steps, np.ceil(opts.sustain_s * 1e3 / kernel_ms))) if opts.sustain_s > 0 else 0
+    sustained = None
+    if sus_steps:
+        clocks2 = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            clocks2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(sus_steps):
+            step()
+        s1.record()
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        c2 = clocks2.stop() if rank == 0 else None
+        sustained = {'steps': sus_steps, 'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / sus_steps,
+                     'value': world * n * sus_steps / (sus_ms * 1e-3), 'clocks': c2}
+
     # -- end to end through the host API
     out_host = torch.empty(n, dtype=torch.float64).pin_memory()
     th_np, out_np = theta_host.numpy(), out_host.numpy()
@@ -270,120 +379,117 @@ def run_gpu(opts):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * n * e2e_steps / e2e_s
     assert np.array_equal(out_np, out.cpu().numpy()), 'host pipeline and device path disagree'
-    # context for e2e: the plain pinned-host -> device copy rate of the same theta buffer (the link ceiling)
+    # context for e2e: the plain pinned-host -> device copy rate of the same theta buffer, measured on ALL ranks AT THE
+    # SAME TIME (barrier first): the contended link ceiling of this box, which the pipeline cannot exceed
     link = 0.0
     for _ in range(3):
+        barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
         theta.copy_(theta_host, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
         link = max(link, theta_host.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    link_min = min_over_ranks(link)
     finite_frac = float(np.isfinite(out_np).mean())
 
     # -- secondary: sharded Monte-Carlo scan with the histogram all-reduce (config 4)
     def _scan_section():
-        scan_info = None
-        if opts.scan_samples > 0:
-            fm = scan.scan_model(opts.scan_mode, dimension=6)
-            scan.scan_histogram(fm, 10 ** 7, nb=25, seed=26)      # warm-up (also NCCL channel set-up)
-            barrier()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            hist, kept = scan.scan_histogram(fm, opts.scan_samples, nb=25, seed=26, return_tensor=True)
-            s1.record()
-            barrier()
-            scan_ms = max_over_ranks(s0.elapsed_time(s1))
-            scan_info = {'mode': opts.scan_mode, 'samples': opts.scan_samples, 'nb': 25, 'seconds': scan_ms * 1e-3,
-                         'samples_per_s': opts.scan_samples / (scan_ms * 1e-3), 'scaling': 'strong',
-                         'kept': int(kept.item()), 'hist_checksum': int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item()),
-                         'collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
-        return scan_info
+        if opts.scan_samples <= 0:
+            return {}
+        fm = scan.scan_model(opts.scan_mode, dimension=6)
+        scan.scan_histogram(fm, 10 ** 7, nb=25, seed=26)      # warm-up (also NCCL channel set-up)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        hist, kept = scan.scan_histogram(fm, opts.scan_samples, nb=25, seed=26, return_tensor=True)
+        s1.record()
+        barrier()
+        scan_ms = max_over_ranks(s0.elapsed_time(s1))
+        checksum = int((hist.flatten() * torch.arange(hist.numel(), device='cuda') % 1000003).sum().item())
+        return {'scan_mode': opts.scan_mode, 'scan_samples': opts.scan_samples, 'scan_nb': 25, 'scan_seconds': scan_ms * 1e-3,
+                'scan_samples_per_s': opts.scan_samples / (scan_ms * 1e-3), 'scan_scaling': 'strong', 'scan_kept': int(kept.item()),
+                'scan_hist_checksum': checksum,
+                'scan_collective': 'one NCCL all-reduce (sum, int64) of the 26^3 histogram' if world > 1 else 'none (1 GPU)'}
 
     try:
         scan_info = _scan_section()
     except Exception as exc:  # noqa: BLE001  (a secondary section must never cost the headline line)
-        scan_info = {'error': repr(exc)}
+        scan_info = {'scan_error': repr(exc)}
 
-    # -- secondary: the sampler-shaped configs of BASELINE.json (latency-bound by design: 512 / 2048 /
-    #    18000 points per half-step), run on the device-resident ensemble sampler
+    # -- secondary: the sampler-shaped configs of BASELINE.json (latency-bound by design: 50 / 512 / 2048 /
+    #    18000 points per half-step), run on the device-resident ensemble sampler, and K1 against HBM
     def _configs_section():
-        cfg_info = None
-        if opts.configs:
-            import models as _m
-            from golemflavor_b200 import mcmc, sens
-            g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
-            cfg_info = {}
+        if not opts.configs:
+            return {}
+        import models as _m
+        from golemflavor_b200 import mcmc, sens
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
+        info = {}
 
-            def timed(fn_):
-                barrier()
-                t0_ = time.perf_counter()
-                r_ = fn_()
-                torch.cuda.synchronize()
-                return max_over_ranks(time.perf_counter() - t0_), r_
+        def timed(fn_):
+            barrier()
+            t0_ = time.perf_counter()
+            r_ = fn_()
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0_), r_
 
-            a2, as2, ps2 = _m.notebook_model(g['asimov_angles'])
-            f2 = llh.LnProb(a2, as2, ps2)
-            np.random.seed(25)
-            p0 = mcmc.flat_seed(ps2, 1024)
-            p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
-            # K1: the SM-only log-posterior (161 algorithmic FLOP / 56 B per point) is HBM-bound: report it against HBM
-            n1 = 1 << 24
-            th1 = torch.as_tensor(_m.draw_in_ranges(ps2, 1 << 20, np.random.default_rng(3))).cuda().repeat(16, 1)
-            o1 = torch.empty(n1, dtype=torch.float64, device='cuda')
-            k1 = lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(th1), n1, 6, 1, _lib.ptr(o1), None, None, stream))
-            for _ in range(3):
-                k1()
-            torch.cuda.synchronize()
-            k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0e.record()
-            for _ in range(20):
-                k1()
-            k1e.record()
-            torch.cuda.synchronize()
-            k1ms = k0e.elapsed_time(k1e) / 20
-            cfg_info['K1_sm_lnprob'] = {'points': n1, 'ms': k1ms, 'evals_per_s': n1 / (k1ms * 1e-3), 'bound': 'hbm',
-                                        'achieved_gbs': 56.0 * n1 / (k1ms * 1e-3) / 1e9,
-                                        'note': '6-D notebook model (4 PMNS coords + 2 source angles), theta 805 MB > L2'}
-            del th1, o1
-            smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
-            smp.run_mcmc(p0, 200, store=False)
-            sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))
-            cfg_info['C2_emcee_sm_fit'] = {'walkers': 1024, 'steps': 10000, 'ndim': 6, 'seconds': sec, 'evals_per_s': 1024 * 1e4 / sec,
-                                           'acceptance': float(np.mean(smp.acceptance_fraction)), 'launches': 1,
-                                           'note': 'replicas only: every rank runs the same chain shape independently'}
-            # C1: the reference's own CPU-sized case (3 raw source ratios, fixed NuFIT PMNS), here on the device sampler
-            a1, as1, ps1 = _m.sm_fit_c1(g['asimov_angles'])
-            f1 = llh.LnProb(a1, as1, ps1)
-            p1 = mcmc.flat_seed(ps1, 100)
-            smp1 = mcmc.DeviceEnsembleSampler(100, 3, f1, seed=25)
-            smp1.run_mcmc(p1, 100, store=False)
-            sec, _ = timed(lambda: smp1.run_mcmc(None, 1000, store=True, return_tensor=True))
-            cfg_info['C1_sm_fit_fixed_pmns'] = {'walkers': 100, 'steps': 1000, 'ndim': 3, 'seconds': sec, 'evals_per_s': 100 * 1000 / sec,
-                                                'acceptance': float(np.mean(smp1.acceptance_fraction)), 'launches': 1}
-            p3 = mcmc.flat_seed(pset, 4096)
-            smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
-            smp3.run_mcmc(p3, 100, store=False)
-            sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
-            cfg_info['C3_bsm_dim6_fit'] = {'walkers': 4096, 'steps': 2000, 'ndim': fn.ndim, 'seconds': sec, 'evals_per_s': 4096 * 2000 / sec,
-                                           'acceptance': float(np.mean(smp3.acceptance_fraction))}
-            sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first cooperative launches, NCCL float64 path)
-            sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
-            cfg_info['C5_sens_sweep'] = {'grid_points': int(len(sw['scale'])), 'walkers': 60, 'steps': 1200, 'seconds': sec,
-                                         'evals_per_s': len(sw['scale']) * 60 * 1200 / sec, 'acceptance': float(sw['acceptance'].mean()),
-                                         'sharding': 'grid points split over %d rank(s), one all-reduce of the summaries' % world}
-            sens.evidence_grid(dimensions=(6,), segments=4, samples=10000)                 # warm-up
-            sec, ev = timed(lambda: sens.evidence_grid(segments=100, samples=1000000))
-            cfg_info['C5_evidence_grid'] = {'grid_points': int(sum(len(v) for v in ev.values())), 'samples_per_point': 1000000, 'seconds': sec,
-                                            'samples_per_s': 6e8 / sec,
-                                            'note': 'Monte-Carlo evidence ln mean(L) per (dimension, scale), what scripts/sens.py gets from MultiNest; '
-                                                    'samples sharded over the ranks, two all-reduces of the 600 (max, sum-exp) slots'}
-        return cfg_info
+        a2, as2, ps2 = _m.notebook_model(g['asimov_angles'])
+        f2 = llh.LnProb(a2, as2, ps2)
+        np.random.seed(25)
+        p0 = mcmc.flat_seed(ps2, 1024)
+        p0[:, 4], p0[:, 5] = np.random.uniform(.9, 1, 1024), np.random.uniform(.8, 1, 1024)
+        # K1: the SM-only log-posterior (161 algorithmic FLOP / 56 B per point) is HBM-bound: report it against HBM
+        n1 = 1 << 24
+        th1 = torch.as_tensor(_m.draw_in_ranges(ps2, 1 << 20, np.random.default_rng(3))).cuda().repeat(16, 1)
+        o1 = torch.empty(n1, dtype=torch.float64, device='cuda')
+        k1 = lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(th1), n1, 6, 1, _lib.ptr(o1), None, None, stream))  # noqa: E731
+        for _ in range(3):
+            k1()
+        torch.cuda.synchronize()
+        k0e, k1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0e.record()
+        for _ in range(20):
+            k1()
+        k1e.record()
+        torch.cuda.synchronize()
+        k1ms = k0e.elapsed_time(k1e) / 20
+        info['k1_sm_lnprob_evals_per_s'] = n1 / (k1ms * 1e-3)
+        info['k1_sm_lnprob_gbs'] = 56.0 * n1 / (k1ms * 1e-3) / 1e9      # 6-D notebook model, theta 805 MB > L2, 56 B / point
+        del th1, o1
+        smp = mcmc.DeviceEnsembleSampler(1024, 6, f2, seed=25)
+        smp.run_mcmc(p0, 200, store=False)
+        sec, _ = timed(lambda: smp.run_mcmc(None, 10000, store=True, return_tensor=True))
+        info['c2_emcee_1024x10000_seconds'] = sec
+        info['c2_acceptance'] = float(np.mean(smp.acceptance_fraction))
+        # C1: the reference's own CPU-sized case (3 raw source ratios, fixed NuFIT PMNS), here on the device sampler
+        a1, as1, ps1 = _m.sm_fit_c1(g['asimov_angles'])
+        f1 = llh.LnProb(a1, as1, ps1)
+        p1 = mcmc.flat_seed(ps1, 100)
+        smp1 = mcmc.DeviceEnsembleSampler(100, 3, f1, seed=25)
+        smp1.run_mcmc(p1, 100, store=False)
+        sec, _ = timed(lambda: smp1.run_mcmc(None, 1000, store=True, return_tensor=True))
+        info['c1_emcee_100x1000_seconds'] = sec
+        p3 = mcmc.flat_seed(pset, 4096)
+        smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
+        smp3.run_mcmc(p3, 100, store=False)
+        sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
+        info['c3_bsm_4096_walkers_us_per_step'] = sec / 2000 * 1e6
+        info['c3_acceptance'] = float(np.mean(smp3.acceptance_fraction))
+        sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first launches, NCCL float64 path)
+        sec, sw = timed(lambda: sens.sweep(segments=100, nwalkers=60, burnin=200, nsteps=1000))
+        info['c5_sweep_600x60x1200_seconds'] = sec      # grid points split over the ranks, one all-reduce of the summaries
+        info['c5_sweep_acceptance'] = float(sw['acceptance'].mean())
+        sens.evidence_grid(dimensions=(6,), segments=4, samples=10000)                 # warm-up
+        sec, ev = timed(lambda: sens.evidence_grid(segments=100, samples=1000000))
+        info['c5_evidence_600x1e6_seconds'] = sec       # Monte-Carlo evidence per (dimension, scale); samples sharded over the ranks
+        info['c5_evidence_samples_per_s'] = 6e8 / sec
+        return info
 
     try:
         cfg_info = _configs_section()
     except Exception as exc:  # noqa: BLE001  (a secondary section must never cost the headline line)
-        cfg_info = {'error': repr(exc)}
+        cfg_info = {'configs_error': repr(exc)}
 
     if rank == 0:
         base = None
@@ -391,39 +497,62 @@ def run_gpu(opts):
             v, total, wall = cpu_baseline(opts.cpu_evals, 1)
             base = {'value': v, 'unit': 'evals/s', 'cores': 1, 'kind': 'port',
                     'sample': '{0} scalar float128 ln_prob evaluations of the same model ({1:.1f} s)'.format(total, wall)}
+            try:
+                base['c2_notebook_model'] = cpu_baseline_c2(max(50, opts.cpu_evals // 3))
+                base['c1_end_to_end'] = cpu_baseline_c1(max(10, opts.cpu_evals // 8))
+            except Exception as exc:  # noqa: BLE001
+                base['secondary_error'] = repr(exc)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
         except (OSError, ValueError):
             pass
         hbm_peak = peaks.get('hbm_gbs', 6650.0)
-        traffic = None
+        prof = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json'))).get('k_lnprob_bytes_per_launch')
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')))
         except (OSError, ValueError):
             pass
-        achieved = FLOP_PER_EVAL * n / (kernel_ms * 1e-3) / 1e12
+        inst = prof.get('k_lnprob_fp64_thread_inst_per_point')      # ncu count for this build (dfma + dmul + dadd + other fp64-pipe)
+        evals_per_s_gpu = n / (kernel_ms * 1e-3)
+        executed = 2.0 * inst * evals_per_s_gpu / 1e12 if inst else None   # TFLOP/s in FMA-issue equivalents (2 per issue slot)
+        algorithmic = FLOP_PER_EVAL * evals_per_s_gpu / 1e12
+        hbm_gbs = BYTES_PER_EVAL * evals_per_s_gpu / 1e9
+        roof = {'bound': 'fp64', 'achieved': executed, 'peak': peak, 'unit': 'TFLOP/s (FMA-issue equivalents: 2 per fp64 instruction)',
+                'frac': executed / peak if executed and peak else None,
+                'traffic': prof.get('k_lnprob_bytes_per_launch'), 'traffic_source': 'ncu --set full, offline (%s)' % prof.get('k_lnprob_bytes_per_launch_source'),
+                'kernel': 'k_lnprob<0,5,1>', 'fp64_inst_per_eval': inst, 'fp64_inst_source': 'ncu, offline (%s)' % prof.get('k_lnprob_fp64_inst_source'),
+                'fp64_pipe_active_pct_ncu': prof.get('k_lnprob_fp64_pipe_pct'),
+                'algorithmic_flop_per_eval': FLOP_PER_EVAL, 'algorithmic_tflops': algorithmic, 'algorithmic_ratio': algorithmic / peak if peak else None,
+                'peak_source': 'DFMA microbenchmark (gf_fp64_peak_probe) in this run; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2',
+                'hbm_gbs': hbm_gbs, 'hbm_frac': hbm_gbs / hbm_peak, 'hbm_peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}
+        if sustained:
+            roof['sustained_seconds'] = sustained['seconds']
+            roof['sustained_ms_per_step'] = sustained['ms_per_step']
+            roof['sustained_value'] = sustained['value']
+            roof['sustained_frac'] = (2.0 * inst * (n / (sustained['ms_per_step'] * 1e-3)) / 1e12 / peak) if inst and peak else None
+            if clock_info is not None and sustained['clocks']:
+                clock_info['sustained'] = {k: sustained['clocks'].get(k) for k in ('sm_mhz', 'sm_min_mhz', 'power_w_max', 'samples', 'reasons')}
+        config = {'workload': WORKLOAD, 'points_per_step_per_gpu': n, 'ndim': fn.ndim, 'nbins': 20,
+                  'parallelism': 'dp%d (independent shards, no data-path collective)' % world,
+                  'l2': 'inputs (235 MB theta per step) larger than the 126 MB L2', 'finite_fraction': finite_frac}
+        config.update(scan_info)
+        config.update(cfg_info)
+        if 'k1_sm_lnprob_gbs' in config:
+            config['k1_hbm_frac'] = config['k1_sm_lnprob_gbs'] / hbm_peak
         line = {
             'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': opts.steps, 'warmup': opts.warmup,
             'ms_per_step': kernel_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'points_per_step_per_gpu': n, 'ndim': fn.ndim, 'nbins': 20, 'parallelism': 'dp%d (independent shards, no data-path collective)' % world,
-                       'l2': 'inputs (235 MB theta per step) larger than the 126 MB L2', 'finite_fraction': finite_frac},
-            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
-                         'traffic': traffic, 'kernel': 'k_lnprob<0>', 'flop_per_eval': FLOP_PER_EVAL,
-                         'peak_source': 'DFMA microbenchmark (gf_fp64_peak_probe) measured in this run; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2',
-                         'hbm': {'achieved': BYTES_PER_EVAL * n / (kernel_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                                 'frac': BYTES_PER_EVAL * n / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                                 'peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}},
+            'config': config,
+            'roofline': roof,
             'cpu_baseline': base,
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': n * fn.ndim * 8, 'd2h_bytes_per_step': n * 8,
-                    'steps': e2e_steps, 'api': 'golemflavor_b200.llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)',
-                    'h2d_gbs': e2e_value / world * fn.ndim * 8 / 1e9, 'h2d_link_gbs': link,
-                    'note': 'bound by the host link: h2d_gbs is the input rate the pipeline sustains per GPU, h2d_link_gbs a plain pinned copy of the same buffer'},
+                    'steps': e2e_steps, 'api': 'llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)',
+                    'h2d_gbs': e2e_value / world * fn.ndim * 8 / 1e9, 'h2d_link_gbs': link, 'h2d_link_gbs_min_over_ranks': link_min,
+                    'numa_node': numa},
             'gpu_launches': int(launches),
             'clocks': clock_info,
-            'scan': scan_info,
-            'configs': cfg_info,
         }
         emit(line)
     if world > 1:
@@ -460,6 +589,7 @@ def main():
     ap.add_argument('--scan-samples', type=int, default=10 ** 10, help='samples of the secondary scan section (0 = skip)')
     ap.add_argument('--configs', type=int, default=1, help='1: also time the sampler-shaped configs C2/C3/C5 (secondary section)')
     ap.add_argument('--scan-mode', default='anarchic', choices=['unitary', 'x', 'texture', 'anarchic'])
+    ap.add_argument('--sustain-s', type=float, default=1.2, help='length of the sustained k_lnprob loop after the K timed steps (0 = skip)')
     opts = ap.parse_args()
     opts.warmup = max(opts.warmup, 3) if opts.impl == 'b200' else opts.warmup
     if opts.impl == 'reference':

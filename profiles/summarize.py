@@ -38,7 +38,20 @@ KEYS = [
     'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sectors_op_atom.sum', 'lts__t_sectors_op_red.sum',
+    'smsp__sass_thread_inst_executed_op_dfma_pred_on.sum.per_cycle_elapsed', 'smsp__sass_thread_inst_executed_op_dmul_pred_on.sum.per_cycle_elapsed',
+    'smsp__sass_thread_inst_executed_op_dadd_pred_on.sum.per_cycle_elapsed', 'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed',
+    'smsp__thread_inst_executed_per_inst_executed.ratio',
 ]
+
+
+def fp64_thread_inst(out):
+    """Executed fp64 arithmetic thread-instructions of the launch: (DFMA + DMUL + DADD per elapsed cycle, summed over
+    the SM sub-partitions) x elapsed cycles -- the `--set full` capture reports the SASS op counters per cycle."""
+    try:
+        per_cycle = sum(out['smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % op]['value'] for op in ('dfma', 'dmul', 'dadd'))
+        return per_cycle * out['sm__cycles_elapsed.avg']['value']
+    except KeyError:
+        return None
 
 
 def launches(tag, path):
@@ -66,7 +79,7 @@ def launches(tag, path):
     print('wrote', tag + '_launches.md')
 
 
-def capture(tag, name, rep, traffic_key=None):
+def capture(tag, name, rep, traffic_key=None, points=0):
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, units, vals = rows[0], rows[1], rows[2]
@@ -97,6 +110,13 @@ def capture(tag, name, rep, traffic_key=None):
         fp = out.get('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed')
         if fp:
             t[traffic_key.replace('bytes_per_launch', 'fp64_pipe_pct')] = fp['value']
+        inst = fp64_thread_inst(out)
+        if inst and points:
+            t[traffic_key.replace('bytes_per_launch', 'fp64_thread_inst_per_point')] = inst / points
+            t[traffic_key.replace('bytes_per_launch', 'fp64_inst_source')] = '%s_%s.json: (dfma + dmul + dadd thread instructions per cycle) x cycles / %d points' % (tag, name, points)
+            for op in ('dfma', 'dmul', 'dadd'):
+                t[traffic_key.replace('bytes_per_launch', op + '_per_point')] = \
+                    out['smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % op]['value'] * out['sm__cycles_elapsed.avg']['value'] / points
         json.dump(t, open(tpath, 'w'), indent=1)
     print('wrote', '%s_%s.md' % (tag, name))
 
@@ -105,11 +125,12 @@ if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('tag')
     ap.add_argument('--launches')
-    ap.add_argument('--rep', action='append', default=[], help='name=path[:traffic_key]')
+    ap.add_argument('--rep', action='append', default=[], help='name=path[:traffic_key[:points per launch]]')
     a = ap.parse_args()
     if a.launches:
         launches(a.tag, a.launches)
     for spec in a.rep:
         name, rest = spec.split('=', 1)
         path, _, key = rest.partition(':')
-        capture(a.tag, name, path, key or None)
+        key, _, pts = key.partition(':')
+        capture(a.tag, name, path, key or None, int(pts or 0))
