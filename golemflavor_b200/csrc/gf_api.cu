@@ -24,14 +24,17 @@ int gf_fail(int code, const char* fmt, ...) {
 }
 
 int gf_sm_count(int* sms) {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, n = 0;
-        GF_CUDA(cudaGetDevice(&dev));
+    /* cached per device ordinal: a process may drive several GPUs */
+    constexpr int kMaxDevices = 64;
+    static std::atomic<int> cached[kMaxDevices];
+    int dev = 0;
+    GF_CUDA(cudaGetDevice(&dev));
+    int n = (dev >= 0 && dev < kMaxDevices) ? cached[dev].load(std::memory_order_relaxed) : 0;
+    if (!n) {
         GF_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-        cached = n;
+        if (dev >= 0 && dev < kMaxDevices) cached[dev].store(n, std::memory_order_relaxed);
     }
-    *sms = cached;
+    *sms = n;
     return GF_OK;
 }
 
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(GF_EW_THREADS)
 
 __global__ void __launch_bounds__(GF_EW_THREADS)
     k_params_to_bsmu(const double* __restrict__ bsm, int dim, const double* __restrict__ energy, const double* __restrict__ mass,
-                     int64_t mass_stride, const double* __restrict__ sm_u, int64_t smu_stride, int no_bsm, int64_t n,
+                     int64_t mass_stride, const double* __restrict__ sm_u, int64_t smu_stride, int no_bsm, double epsilon, int64_t n,
                      double* __restrict__ vec, uint8_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -309,6 +312,24 @@ __global__ void __launch_bounds__(GF_EW_THREADS)
         acc += fabs(v[k]);
     }
     if (!(acc < 1e300)) st |= GFP_ST_NON_FINITE | GFP_ST_NON_UNITARY;
+    /* fr.test_unitarity (fr.py:489-498): f = |V V^+|, |tr f - 3| and |sum f - 3| against epsilon */
+    double tr = 0.0, sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            double re = 0.0, im = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double ar = v[2 * (3 * a + c)], ai = v[2 * (3 * a + c) + 1], br = v[2 * (3 * b + c)], bi = v[2 * (3 * b + c) + 1];
+                re += ar * br + ai * bi;
+                im += ai * br - ar * bi;
+            }
+            const double f = sqrt(re * re + im * im);
+            sum += f;
+            if (a == b) tr += f;
+        }
+    if (!(fabs(tr - 3.0) < epsilon && fabs(sum - 3.0) < epsilon)) st |= GFP_ST_NON_UNITARY;
     if (status) status[i] = (uint8_t)st;
 }
 
@@ -455,7 +476,8 @@ extern "C" int gf_eigvec_herm3(const double* d_ham, int64_t n, double* d_vec, do
 extern "C" int gf_params_to_bsmu(const double* d_bsm, int32_t dim, const double* d_energy, const double* d_mass, int64_t mass_stride,
                                  const double* d_sm_u, int64_t smu_stride, int32_t no_bsm, double epsilon, int64_t n, double* d_vec,
                                  uint8_t* d_status, void* stream) {
-    (void)epsilon; /* the Jacobi eigenvector matrix is unitary to rounding by construction */
+    if (!(epsilon > 0.0)) epsilon = 1e-7; /* fr.py:319 default; the Jacobi eigenvectors are unitary to rounding, so only a
+                                            * caller-tightened epsilon (or a non-finite input) ever raises the flag */
     GF_REQUIRE(n >= 0, "gf_params_to_bsmu: n = %lld", (long long)n);
     GF_REQUIRE(mass_stride == 0 || mass_stride == 2, "gf_params_to_bsmu: mass_stride must be 0 or 2");
     GF_REQUIRE(smu_stride == 0 || smu_stride == 18, "gf_params_to_bsmu: smu_stride must be 0 or 18");
@@ -463,7 +485,7 @@ extern "C" int gf_params_to_bsmu(const double* d_bsm, int32_t dim, const double*
     if (n == 0) return GF_OK;
     GF_REQUIRE(d_energy && d_mass && d_sm_u && d_vec && (no_bsm || d_bsm), "gf_params_to_bsmu: null pointer");
     k_params_to_bsmu<<<gf_blocks_for(n, GF_EW_THREADS), GF_EW_THREADS, 0, (cudaStream_t)stream>>>(
-        d_bsm, dim, d_energy, d_mass, mass_stride, d_sm_u, smu_stride, no_bsm, n, d_vec, d_status);
+        d_bsm, dim, d_energy, d_mass, mass_stride, d_sm_u, smu_stride, no_bsm, epsilon, n, d_vec, d_status);
     ++g_gf_launches;
     GF_LAUNCH_CHECK("k_params_to_bsmu");
     return GF_OK;

@@ -174,9 +174,11 @@ constexpr int kSlots = 3;               /* H2D of chunk c+1 and D2H of chunk c-1
 #define GF_HOST_CHUNK_LOG2 18
 #endif
 constexpr int64_t kChunkPoints = 1ll << GF_HOST_CHUNK_LOG2;
+constexpr int kMaxPipeDevices = 64;
 
+/* One pipeline per device ordinal (a process may drive several GPUs); created on first use, kept for the
+ * life of the process. */
 struct HostPipe {
-    int device = -1;
     cudaStream_t stream[kSlots] = {};
     cudaEvent_t done[kSlots] = {};
     double* d_theta[kSlots] = {};
@@ -188,17 +190,33 @@ struct HostPipe {
     double* s_lnp[kSlots] = {};
     double* s_fr[kSlots] = {};
     uint8_t* s_st[kSlots] = {};
-    bool ready = false;
+    bool ready = false, staged = false;
 };
 
 std::mutex g_pipe_mutex;
-HostPipe g_pipe;
+HostPipe g_pipes[kMaxPipeDevices];
 
-int pipe_init(HostPipe& p) {
-    int dev = 0;
-    GF_CUDA(cudaGetDevice(&dev));
-    if (p.ready && p.device == dev) return GF_OK;
-    GF_REQUIRE(!p.ready, "gf_lnprob_host: the host pipeline is bound to device %d, current device is %d", p.device, dev);
+void pipe_release(HostPipe& p) {
+    for (int s = 0; s < kSlots; ++s) {
+        if (p.stream[s]) cudaStreamDestroy(p.stream[s]);
+        if (p.done[s]) cudaEventDestroy(p.done[s]);
+        cudaFree(p.d_theta[s]);
+        cudaFree(p.d_lnp[s]);
+        cudaFree(p.d_fr[s]);
+        cudaFree(p.d_st[s]);
+    }
+    cudaGetLastError();
+    const HostPipe fresh;
+    /* staging buffers (if any) survive: they are host memory, independent of what failed */
+    double* st[kSlots]; double* sl[kSlots]; double* sf[kSlots]; uint8_t* ss[kSlots];
+    for (int s = 0; s < kSlots; ++s) { st[s] = p.s_theta[s]; sl[s] = p.s_lnp[s]; sf[s] = p.s_fr[s]; ss[s] = p.s_st[s]; }
+    const bool staged = p.staged;
+    p = fresh;
+    for (int s = 0; s < kSlots; ++s) { p.s_theta[s] = st[s]; p.s_lnp[s] = sl[s]; p.s_fr[s] = sf[s]; p.s_st[s] = ss[s]; }
+    p.staged = staged;
+}
+
+int pipe_init_unchecked(HostPipe& p) {
     for (int s = 0; s < kSlots; ++s) {
         GF_CUDA(cudaStreamCreateWithFlags(&p.stream[s], cudaStreamNonBlocking));
         GF_CUDA(cudaEventCreateWithFlags(&p.done[s], cudaEventDisableTiming));
@@ -207,7 +225,16 @@ int pipe_init(HostPipe& p) {
         GF_CUDA(cudaMalloc(&p.d_fr[s], kChunkPoints * 3 * sizeof(double)));
         GF_CUDA(cudaMalloc(&p.d_st[s], kChunkPoints));
     }
-    p.device = dev;
+    return GF_OK;
+}
+
+int pipe_init(HostPipe& p) {
+    if (p.ready) return GF_OK;
+    const int rc = pipe_init_unchecked(p);
+    if (rc != GF_OK) {
+        pipe_release(p); /* nothing half-built is kept: the next call starts from scratch */
+        return rc;
+    }
     p.ready = true;
     return GF_OK;
 }
@@ -223,31 +250,22 @@ bool is_pinned(const void* ptr) {
 }
 
 int staging_init(HostPipe& p) {
-    if (p.s_theta[0]) return GF_OK;
+    if (p.staged) return GF_OK;
     for (int s = 0; s < kSlots; ++s) {
-        GF_CUDA(cudaHostAlloc(&p.s_theta[s], kChunkPoints * GF_MAX_DIM * sizeof(double), cudaHostAllocDefault));
-        GF_CUDA(cudaHostAlloc(&p.s_lnp[s], kChunkPoints * sizeof(double), cudaHostAllocDefault));
-        GF_CUDA(cudaHostAlloc(&p.s_fr[s], kChunkPoints * 3 * sizeof(double), cudaHostAllocDefault));
-        GF_CUDA(cudaHostAlloc(&p.s_st[s], kChunkPoints, cudaHostAllocDefault));
+        if (!p.s_theta[s]) GF_CUDA(cudaHostAlloc(&p.s_theta[s], kChunkPoints * GF_MAX_DIM * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_lnp[s]) GF_CUDA(cudaHostAlloc(&p.s_lnp[s], kChunkPoints * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_fr[s]) GF_CUDA(cudaHostAlloc(&p.s_fr[s], kChunkPoints * 3 * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_st[s]) GF_CUDA(cudaHostAlloc(&p.s_st[s], kChunkPoints, cudaHostAllocDefault));
     }
+    p.staged = true;
     return GF_OK;
 }
 
-}  // namespace
-
-extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int64_t n, double* h_lnprob, double* h_fr, uint8_t* h_status) {
-    gf_dev_model d;
-    if (int rc = gf_build_dev_model(model, &d)) return rc;
-    GF_REQUIRE(n >= 0, "gf_lnprob_host: n = %lld", (long long)n);
-    if (n == 0) return GF_OK;
-    GF_REQUIRE(h_theta && h_lnprob, "gf_lnprob_host: null pointer");
-    std::lock_guard<std::mutex> lock(g_pipe_mutex);
-    HostPipe& p = g_pipe;
-    if (int rc = pipe_init(p)) return rc;
-    const bool direct = is_pinned(h_theta) && is_pinned(h_lnprob) && is_pinned(h_fr) && is_pinned(h_status);
-    if (!direct)
-        if (int rc = staging_init(p)) return rc;
+/* the chunk loop proper; on an error return copies may still be in flight -- the caller quiesces the streams */
+int pipe_run(HostPipe& p, const gf_dev_model& d, bool direct, const double* h_theta, int64_t n, double* h_lnprob, double* h_fr,
+             uint8_t* h_status) {
     const int ndim = d.ndim;
+    const int spec = gf_model_spec(d);
     const int64_t nchunks = (n + kChunkPoints - 1) / kChunkPoints;
     /* results of chunk c staged in slot c % kSlots are copied out before the slot is reused */
     auto drain = [&](int64_t c) -> int {
@@ -273,7 +291,7 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
         }
         GF_CUDA(cudaMemcpyAsync(p.d_theta[s], src, cnt * ndim * sizeof(double), cudaMemcpyHostToDevice, p.stream[s]));
         const gf_theta_view th{p.d_theta[s], ndim, 1};
-        launch_lnprob<GF_K_LNPROB>(d, gf_model_spec(d), th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr, p.stream[s]);
+        launch_lnprob<GF_K_LNPROB>(d, spec, th, cnt, p.d_lnp[s], h_fr ? p.d_fr[s] : nullptr, h_status ? p.d_st[s] : nullptr, p.stream[s]);
         ++g_gf_launches;
         GF_LAUNCH_CHECK("gf_lnprob_host");
         GF_CUDA(cudaMemcpyAsync(direct ? h_lnprob + off : p.s_lnp[s], p.d_lnp[s], cnt * sizeof(double), cudaMemcpyDeviceToHost, p.stream[s]));
@@ -286,4 +304,31 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
     for (int64_t c = (nchunks > kSlots ? nchunks - kSlots : 0); c < nchunks; ++c)
         if (int rc = drain(c)) return rc;
     return GF_OK;
+}
+
+}  // namespace
+
+extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int64_t n, double* h_lnprob, double* h_fr, uint8_t* h_status) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    GF_REQUIRE(n >= 0, "gf_lnprob_host: n = %lld", (long long)n);
+    if (n == 0) return GF_OK;
+    GF_REQUIRE(h_theta && h_lnprob, "gf_lnprob_host: null pointer");
+    int dev = 0;
+    GF_CUDA(cudaGetDevice(&dev));
+    GF_REQUIRE(dev >= 0 && dev < kMaxPipeDevices, "gf_lnprob_host: device ordinal %d outside [0, %d)", dev, kMaxPipeDevices);
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    HostPipe& p = g_pipes[dev];
+    if (int rc = pipe_init(p)) return rc;
+    const bool direct = is_pinned(h_theta) && is_pinned(h_lnprob) && is_pinned(h_fr) && is_pinned(h_status);
+    if (!direct)
+        if (int rc = staging_init(p)) return rc;
+    const int rc = pipe_run(p, d, direct, h_theta, n, h_lnprob, h_fr, h_status);
+    if (rc != GF_OK) {
+        /* the caller is about to be told that the call failed: no copy may still be writing into its buffers
+         * (or reading the staging ring) after we return */
+        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(p.stream[s]);
+        cudaGetLastError();
+    }
+    return rc;
 }

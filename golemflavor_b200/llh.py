@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 from . import model as _model
 
-__all__ = ['GaussianBoundedRV', 'multi_gaussian', 'lnprior', 'triangle_llh', 'ln_prob', 'LnProb']
+__all__ = ['GaussianBoundedRV', 'multi_gaussian', 'lnprior', 'triangle_llh', 'ln_prob', 'LnProb', 'prepared']
 
 
 def _is_tensor(x):
@@ -166,7 +166,7 @@ def triangle_llh(theta, args, asimov_paramset, llh_paramset):
     GolemFit): llh = multi_gaussian(measured fr(theta), injected fr, smearing)."""
     _check_len(theta, llh_paramset, closing=']')
     torch = _lib.torch_cuda()
-    fn = LnProb(args, asimov_paramset, llh_paramset)
+    fn = prepared(args, asimov_paramset, llh_paramset)
     th = _lib.to_device(theta, torch, fn.ndim)
     batched = th.ndim > 1
     th2 = th.reshape(-1, fn.ndim)
@@ -189,9 +189,42 @@ def triangle_llh(theta, args, asimov_paramset, llh_paramset):
     return out if batched else float(out[0])
 
 
+_PREPARED = {}
+
+
+def _fingerprint(args, asimov_paramset, llh_paramset):
+    """Everything ``model.flatten`` reads, as a hashable key: the reference calls ``ln_prob`` with the same three
+    closure arguments millions of times (``scripts/fr.py:182-187``), so the flattened model is cached -- but keyed by
+    CONTENT, because the reference's own code mutates ``Param.value`` / ``args`` between calls."""
+    def num(x):
+        if x is None:
+            return None
+        a = np.asarray(x, dtype=np.float64)
+        return float(a) if a.ndim == 0 else a.tobytes()
+    pkey = tuple((p.name, num(p.ranges), num(p.nominal_value), num(p.std), str(p.prior), str(p.tag)) for p in llh_paramset)
+    akey = tuple((p.name, num(p.value), num(p.std), str(p.tag)) for p in (asimov_paramset or ()))
+    names = ('source_ratio', 'no_bsm', 'fixed_scale', 'texture', 'dimension', 'binning', 'likelihood', 'llh_const',
+             'injected_ratio', 'smearing', 'llh_offset', 'emulate_underflow')
+    gkey = tuple(num(getattr(args, k)) if k in ('source_ratio', 'binning', 'injected_ratio', 'fixed_scale', 'smearing', 'llh_const', 'llh_offset')
+                 and getattr(args, k, None) is not None else str(getattr(args, k, None)) for k in names)
+    return pkey, akey, gkey
+
+
+def prepared(args, asimov_paramset, llh_paramset):
+    """The cached ``LnProb`` of a closure (a few entries, oldest dropped first)."""
+    key = _fingerprint(args, asimov_paramset, llh_paramset)
+    fn = _PREPARED.get(key)
+    if fn is None:
+        if len(_PREPARED) >= 16:
+            _PREPARED.pop(next(iter(_PREPARED)))
+        fn = _PREPARED[key] = LnProb(args, asimov_paramset, llh_paramset)
+    return fn
+
+
 def ln_prob(theta, args, asimov_paramset, llh_paramset):
     """lnprior + triangle_llh with the -inf short-circuit (``llh.py:121-130``), fused into one kernel.
 
-    No deep copies are needed (``llh.py:122-123``): nothing on the device path mutates the ParamSets."""
+    No deep copies are needed (``llh.py:122-123``): nothing on the device path mutates the ParamSets.  The flattened
+    model is cached across calls (``prepared``), so a call costs one fingerprint of the closure plus one launch."""
     _check_len(theta, llh_paramset)
-    return LnProb(args, asimov_paramset, llh_paramset)(theta)
+    return prepared(args, asimov_paramset, llh_paramset)(theta)

@@ -296,15 +296,36 @@ def _as_lnprob_object(ln_prob):
     return None
 
 
-def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=True, seed=None, device=None):
-    """Run burn-in, reset, run, flatten walker-major (``mcmc.py:27-53``).  Returns ``samples[nwalkers*nsteps, ndim]``."""
+def _accepts_batches(ln_prob, p0):
+    """Probe a foreign callable once with a 2-row batch: a reference-style scalar ``ln_prob(theta[ndim])`` raises or
+    returns something that is not ``[2]`` -- it is then mapped over the walkers like emcee-2 does."""
+    try:
+        out = ln_prob(p0[:2])
+        out = out.detach().cpu().numpy() if hasattr(out, 'detach') else np.asarray(out, dtype=np.float64)
+        return out.shape == (2,)
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=None, seed=None, device=None):
+    """Run burn-in, reset, run, flatten walker-major (``mcmc.py:27-53``).  Returns ``samples[nwalkers*nsteps, ndim]``.
+
+    ``ln_prob`` = an ``llh.LnProb`` or a ``functools.partial`` of ``llh.ln_prob`` runs on the device-resident sampler
+    (``seed=None`` draws a fresh 63-bit seed and prints it); any other callable runs on the bundled host sampler,
+    batched if it accepts ``theta[n, ndim]`` (``vectorize=None`` probes it once), else one walker per call."""
     fn = _as_lnprob_object(ln_prob) if device in (None, True) else None
     if device is True and fn is None:
         raise ValueError('device=True needs an llh.LnProb or a partial of llh.ln_prob')
     if fn is not None:
         # device-resident sampler: proposal + log-posterior + accept in one kernel, no host loop
-        sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, seed=0 if seed is None else seed)
+        if seed is None:
+            # the reference never seeds emcee (mcmc.py:29-31): independent runs must use independent streams
+            seed = int.from_bytes(os.urandom(8), 'little') >> 1
+            print('device sampler seed', seed)
+        sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, seed=seed)
     else:
+        if vectorize is None:
+            vectorize = _accepts_batches(ln_prob, np.asarray(p0, dtype=np.float64))
         sampler = EnsembleSampler(nwalkers, ndim, ln_prob, threads=threads, vectorize=vectorize, seed=seed)
     print("Running burn-in")
     pos = np.asarray(p0)

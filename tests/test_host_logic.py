@@ -513,3 +513,27 @@ def test_bench_reference_arm_prints_one_contract_line():
     gpu = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True, env=env, timeout=600)
     assert gpu.returncode != 0 and 'no CUDA device' in (gpu.stderr + gpu.stdout)
+
+
+def test_mcmc_driver_probes_scalar_callables(capsys):
+    """A reference-style scalar ln_prob(theta[ndim]) (mcmc.py:29-31 hands such a callable to emcee) is mapped over the
+    walkers; a batched callable is called once per half-ensemble."""
+    calls = {'scalar': 0, 'batch': 0}
+
+    def scalar(theta):
+        calls['scalar'] += 1
+        x, y = theta            # raises for a batch
+        return -0.5 * (x * x + y * y)
+
+    def batch(theta):
+        calls['batch'] += 1
+        theta = np.atleast_2d(theta)
+        return -0.5 * (theta ** 2).sum(axis=1)
+
+    np.random.seed(1)
+    p0 = np.random.normal(size=(8, 2))
+    s1 = mcmc.mcmc(p0, scalar, 2, 8, 5, 10, seed=3)
+    s2 = mcmc.mcmc(p0, batch, 2, 8, 5, 10, seed=3)
+    capsys.readouterr()
+    assert s1.shape == s2.shape == (80, 2) and np.allclose(s1, s2)
+    assert calls['scalar'] > 8 * 15 and calls['batch'] < 2 * 15 + 5
