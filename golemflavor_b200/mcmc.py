@@ -297,12 +297,13 @@ def _as_lnprob_object(ln_prob):
 
 
 def _accepts_batches(ln_prob, p0):
-    """Probe a foreign callable once with a 2-row batch: a reference-style scalar ``ln_prob(theta[ndim])`` raises or
+    """Probe a foreign callable once with a 2-row (3-row for ndim = 2) batch: a reference-style scalar ``ln_prob(theta[ndim])`` raises or
     returns something that is not ``[2]`` -- it is then mapped over the walkers like emcee-2 does."""
+    rows = 3 if p0.shape[-1] == 2 else 2     # a row count different from ndim: `x, y = theta` must not unpack rows
     try:
-        out = ln_prob(p0[:2])
+        out = ln_prob(p0[:rows])
         out = out.detach().cpu().numpy() if hasattr(out, 'detach') else np.asarray(out, dtype=np.float64)
-        return out.shape == (2,)
+        return out.shape == (rows,)
     except Exception:  # noqa: BLE001
         return False
 
