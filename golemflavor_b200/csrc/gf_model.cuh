@@ -97,6 +97,7 @@ struct gf_point {
      (SPEC) == GF_SPEC_NPFREE11 ? 11 : (SPEC) == GF_SPEC_SM5X ? 5 : 0)
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
+GF_HD bool gf_model_has_fixed_source(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
 
 /* the general case: runtime column map */
@@ -304,6 +305,58 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
     }
     if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
     return st;
+}
+
+/*
+ * The binned BSM composition of ONE point at SEVERAL new-physics scales (the sensitivity grid of
+ * scripts/sens.py:232-294 evaluates the same prior sample at every grid value of log10(Lambda)): everything that does not
+ * depend on the scale -- the PMNS columns, H0, the new-physics matrix T and the pencil coefficients -- is built once, then
+ * `emit(s, fr, status)` is called with the composition at lam_of(s) = 10^logLam_s for s = 0 .. ns-1.  Same arithmetic per
+ * scale as gf_point_fr (which is the ns = 1 case with lam = exp10(q.loglam)).
+ */
+template <int SPEC, int ILP, class LamOf, class Emit>
+GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, LamOf lam_of, Emit emit) {
+    static_assert(!GF_SPEC_IS_SM(SPEC), "the scale grid needs the BSM path");
+    const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
+    const gfp_cols12 u = gfp_cols_from_trig(t);
+    const double m1 = q.mass[0] * GFP_MASS_SCALE, m2 = q.mass[1] * GFP_MASS_SCALE;
+    gfp_herm3 h0 = gfp_herm_from_cols(u, m1, m2);
+    auto finish = [&](int s, unsigned st, double* fr) {
+        const double mn = fmin(fr[0], fmin(fr[1], fr[2]));
+        if (!(mn >= -m.epsilon)) st |= GFP_ST_NON_UNITARY;
+        if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
+        emit(s, fr, st);
+    };
+    if (GF_SPEC_IS_FIXED(SPEC)) {
+        gfp_herm3 T = m.T;
+        const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
+        for (int s = 0; s < ns; ++s) {
+            double fr[3];
+            const unsigned st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            finish(s, st, fr);
+        }
+    } else {
+        gfp_herm3 T;
+        const bool npf = GF_SPEC_IS_NPFREE(SPEC) || m.np_free;
+        if (npf) {
+            const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
+            T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
+        } else {
+            T = m.T;
+        }
+        const gfp_pencil_T pt = gfp_make_pencil_T(T);
+        const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, npf ? gfp_adj_tf(pt.te, T) : m.adjT);
+        const bool fixed_src = GF_SPEC_IS_NPFREE(SPEC) || gf_model_has_fixed_source(m);
+        const double S = fixed_src ? m.src_S : q.src[0] + q.src[1] + q.src[2];
+        const double s2 = fixed_src ? m.fixed_src[2] : q.src[2];
+        const double sd0 = fixed_src ? m.src_sd0 : q.src[0] - q.src[2], sd1 = fixed_src ? m.src_sd1 : q.src[1] - q.src[2];
+        const double inv_norm = fixed_src ? m.inv_S_wsum : gfp_rcp(S * m.wsum);
+        for (int s = 0; s < ns; ++s) {
+            double fr[3];
+            const unsigned st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam_of(s), s2, sd0, sd1, inv_norm, S, fr);
+            finish(s, st, fr);
+        }
+    }
 }
 
 GF_HD bool gf_model_has_fixed_source(const gf_dev_model& m) { return m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0; }

@@ -404,3 +404,175 @@ extern "C" int gf_scan_evidence(const gf_model* model, const gf_scan_config* cfg
     if (e != cudaSuccess) return gf_fail(GF_ERR_CUDA, "gf_scan_evidence: %s", cudaGetErrorString(e));
     return GF_OK;
 }
+
+/* ------------------------------------------------------------------ evidence on a grid of scales */
+
+/*
+ * The sensitivity grid (scripts/sens.py:232-294: one MultiNest run per (dimension, scale)) as ONE launch per
+ * dimension: blockIdx.y selects a group of `s_per` grid scales, blockIdx.x strides over the prior samples.  A thread
+ * draws its sample once, builds everything that does not depend on the scale once (PMNS, H0, pencil coefficients) and
+ * evaluates the 20-bin composition + likelihood at each scale of the group.  The running log-sum-exp (max, sum) of
+ * every (thread, scale) lives in shared memory (two LDS/STS per ~1900 fp64 instructions), so the accumulators cost no
+ * registers.  Per-block partials are merged by the LAST block of the group (ticket counter) in block order:
+ * deterministic for a given launch geometry, no finishing kernel, no allocation.
+ */
+#define GF_EVG_MAX_S_PER 16
+
+template <int SPEC, bool STATIC6>
+__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SCAN_MIN_BLOCKS)
+    k_evidence_grid(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
+                    const double* __restrict__ scales, const int nscales, const int s_per, double* __restrict__ partials /*[nscales][gridDim.x][2]*/,
+                    unsigned int* __restrict__ tickets /*[gridDim.y]*/, double* __restrict__ lse /*[nscales][2]*/) {
+    extern __shared__ double sh_evg[];
+    constexpr int T = GF_SCAN_THREADS, W = GF_SCAN_THREADS / 32;
+    double* sh_lam = sh_evg;                        /* [GF_EVG_MAX_S_PER]        */
+    double* sh_m = sh_evg + GF_EVG_MAX_S_PER;       /* [s_per][T] running max    */
+    double* sh_s = sh_m + s_per * T;                /* [s_per][T] running sum    */
+    __shared__ double sh_wm[GF_EVG_MAX_S_PER][W], sh_ws[GF_EVG_MAX_S_PER][W];
+    __shared__ int sh_last;
+    const int tid = threadIdx.x, g = blockIdx.y;
+    const int s0 = g * s_per, ns = min(s_per, nscales - s0);
+    if (tid < ns) sh_lam[tid] = exp10(scales[s0 + tid]); /* the same exp10 the per-point kernels apply to logLam */
+    for (int k = 0; k < ns; ++k) {
+        sh_m[k * T + tid] = -INFINITY;
+        sh_s[k * T + tid] = 0.0;
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * T;
+    for (uint64_t j = (uint64_t)blockIdx.x * T + tid; j < count; j += stride) {
+        double theta[GF_MAX_DIM];
+        gf_point q;
+        if constexpr (STATIC6) { /* the layout of sens.py: columns 0-3 mixing coordinates, 4-5 mass splittings */
+            gf_draw_theta<true, 6>(m, seed, first_index + j, theta);
+            q.sm[0] = theta[0]; q.sm[1] = theta[1]; q.sm[2] = theta[2]; q.sm[3] = theta[3];
+            q.mass[0] = theta[4]; q.mass[1] = theta[5];
+        } else {
+            gf_draw_theta(m, seed, first_index + j, theta);
+            gf_resolve_point<SPEC>(m, [&](int k) { return theta[k]; }, q);
+        }
+        gf_point_fr_scales<SPEC, GF_SCAN_ILP_FOR(SPEC)>(
+            m, q, ns, [&](int k) { return sh_lam[k]; },
+            [&](int k, const double* fr, unsigned) {
+                const double ll = m.llh_kind == GF_LLH_FLAT
+                                      ? m.llh_const
+                                      : gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
+                if (ll > -INFINITY) { /* NaN and -inf (pdf underflow) carry no weight */
+                    double mo = sh_m[k * T + tid], so = sh_s[k * T + tid];
+                    const double d = ll - mo;        /* +inf on the first sample */
+                    const double e = exp(-fabs(d));
+                    if (d <= 0.0) {
+                        so += e;
+                    } else {
+                        so = fma(so, e, 1.0);
+                        mo = ll;
+                    }
+                    sh_m[k * T + tid] = mo;
+                    sh_s[k * T + tid] = so;
+                }
+            });
+    }
+    /* block reduction: lanes by shuffle, warps in order */
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int k = 0; k < ns; ++k) {
+        double mx = sh_m[k * T + tid], sm = sh_s[k * T + tid];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double m2 = __shfl_down_sync(0xffffffffu, mx, o), s2 = __shfl_down_sync(0xffffffffu, sm, o);
+            gf_lse_merge(mx, sm, m2, s2);
+        }
+        if (lane == 0) {
+            sh_wm[k][warp] = mx;
+            sh_ws[k][warp] = sm;
+        }
+    }
+    __syncthreads();
+    if (tid < ns) {
+        double mx = sh_wm[tid][0], sm = sh_ws[tid][0];
+        for (int w = 1; w < W; ++w) gf_lse_merge(mx, sm, sh_wm[tid][w], sh_ws[tid][w]);
+        double* out = partials + 2 * ((size_t)(s0 + tid) * gridDim.x + blockIdx.x);
+        out[0] = mx;
+        out[1] = sm;
+    }
+    /* the last block of this scale group merges the per-block partials (classic ticket pattern) */
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh_last = atomicAdd(&tickets[g], 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    if (tid < ns) {
+        double mx = lse[2 * (s0 + tid)], sm = lse[2 * (s0 + tid) + 1];
+        const volatile double* in = partials + 2 * (size_t)(s0 + tid) * gridDim.x;
+        for (unsigned b = 0; b < gridDim.x; ++b) gf_lse_merge(mx, sm, in[2 * b], in[2 * b + 1]); /* block order: deterministic */
+        lse[2 * (s0 + tid)] = mx;
+        lse[2 * (s0 + tid) + 1] = sm;
+    }
+    if (tid == 0) tickets[g] = 0u; /* the workspace is reusable by the next launch on this stream */
+}
+
+namespace {
+
+struct evg_geometry {
+    int s_per, ny, per_sm;
+    unsigned nx;
+    size_t smem;
+};
+
+template <class K>
+int evg_plan(K kern, int nscales, uint64_t count, evg_geometry* geo) {
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    /* scales per block: as many as amortise the per-sample set-up while every SM still gets work; 10 scales
+     * (20 KB of accumulators per block... 2 x 10 x 256 x 8 B = 40 KB) leave two blocks per SM */
+    int s_per = nscales < 10 ? nscales : 10;
+    const size_t smem = (size_t)(GF_EVG_MAX_S_PER + 2 * s_per * GF_SCAN_THREADS) * sizeof(double);
+    GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GF_SCAN_THREADS, smem));
+    GF_REQUIRE(per_sm >= 1, "gf_scan_evidence_grid: kernel does not fit on an SM (smem %zu B)", smem);
+    const int ny = (nscales + s_per - 1) / s_per;
+    const uint64_t want = (count + GF_SCAN_THREADS - 1) / GF_SCAN_THREADS;
+    uint64_t nx = ((uint64_t)sms * per_sm + ny - 1) / ny;
+    if (nx > want) nx = want;
+    if (nx < 1) nx = 1;
+    geo->s_per = s_per; geo->ny = ny; geo->per_sm = per_sm; geo->nx = (unsigned)nx; geo->smem = smem;
+    return GF_OK;
+}
+
+}  // namespace
+
+extern "C" uint64_t gf_scan_evidence_grid_workspace(int32_t nscales) {
+    int sms = 0;
+    if (nscales < 1 || gf_sm_count(&sms) != GF_OK) return 0;
+    /* [nscales][blocks in x][2] partials (blocks in x <= resident blocks of the device) + one ticket per scale */
+    return (uint64_t)nscales * ((uint64_t)sms * 8) * 2 * sizeof(double) + (uint64_t)nscales * sizeof(unsigned int) + 256;
+}
+
+extern "C" int gf_scan_evidence_grid(const gf_model* model, const gf_scan_config* cfg, const double* d_scales, int32_t nscales,
+                                     double* d_lse, void* d_work, uint64_t work_bytes, void* stream) {
+    GF_REQUIRE(cfg != nullptr && d_lse != nullptr && d_scales != nullptr, "gf_scan_evidence_grid: null pointer");
+    GF_REQUIRE(nscales >= 1 && nscales <= 65535, "gf_scan_evidence_grid: nscales = %d outside [1, 65535]", nscales);
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    GF_REQUIRE(!d.no_bsm, "gf_scan_evidence_grid: the model has no BSM path (no_bsm = 1)");
+    GF_REQUIRE(d.col_scale < 0, "gf_scan_evidence_grid: the scale must not be a sampled column (col_scale = %d): it is frozen at the grid values", d.col_scale);
+    if (cfg->count == 0) return GF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool fixed = gf_model_is_fixed_spec(d);
+    const bool static6 = fixed && d.ndim == 6 && d.col_sm[0] == 0 && d.col_sm[1] == 1 && d.col_sm[2] == 2 && d.col_sm[3] == 3 &&
+                         d.col_mass[0] == 4 && d.col_mass[1] == 5;
+    auto kern = static6 ? k_evidence_grid<GF_SPEC_FIXED, true> : fixed ? k_evidence_grid<GF_SPEC_FIXED, false> : k_evidence_grid<GF_SPEC_GENERIC, false>;
+    evg_geometry geo;
+    if (int rc = evg_plan(kern, nscales, cfg->count, &geo)) return rc;
+    const size_t part_bytes = (size_t)nscales * geo.nx * 2 * sizeof(double);
+    const size_t need = part_bytes + (size_t)geo.ny * sizeof(unsigned int);
+    GF_REQUIRE(d_work != nullptr && work_bytes >= need, "gf_scan_evidence_grid: workspace of %llu B is too small, need %llu B (gf_scan_evidence_grid_workspace)",
+               (unsigned long long)work_bytes, (unsigned long long)need);
+    double* part = static_cast<double*>(d_work);
+    unsigned int* tickets = reinterpret_cast<unsigned int*>(static_cast<char*>(d_work) + part_bytes);
+    GF_CUDA(cudaMemsetAsync(tickets, 0, (size_t)geo.ny * sizeof(unsigned int), st));
+    kern<<<dim3(geo.nx, (unsigned)geo.ny), GF_SCAN_THREADS, geo.smem, st>>>(d, cfg->seed, cfg->first_index, cfg->count, d_scales, nscales, geo.s_per, part,
+                                                                              tickets, d_lse);
+    ++g_gf_launches;
+    GF_LAUNCH_CHECK("gf_scan_evidence_grid");
+    return GF_OK;
+}

@@ -21,7 +21,7 @@ from .enums import ParamTag, PriorsCateg, Texture, enum_name
 from .param import Param, ParamSet
 
 __all__ = ['sm_paramset', 'scan_paramset', 'scan_model', 'scan_histogram', 'scan_samples', 'ternary_histogram',
-           'shard_range', 'allreduce_counts', 'coverage_mask', 'scan_evidence']
+           'shard_range', 'allreduce_counts', 'coverage_mask', 'scan_evidence', 'scan_evidence_grid']
 
 DEFAULT_BINNING = np.logspace(np.log10(6e4), np.log10(1e7), 21)  # fr.py:283-285
 
@@ -205,3 +205,32 @@ def scan_evidence(fm, count, seed=26, first_index=0, distributed=True):
         lse = torch.cat([gmax, part])
     m, s = (float(x) for x in lse.cpu())
     return m + np.log(s) - np.log(count) if s > 0 else -np.inf
+
+
+def scan_evidence_grid(fm, scales, count, seed=26, first_index=0, distributed=True):
+    """``scan_evidence`` at every frozen scale of ``scales`` (log10 Lambda) in ONE launch: each prior sample is drawn once
+    and evaluated at all scales (``gf_scan_evidence_grid``; ``scripts/sens.py:199-201, 232-294`` runs one MultiNest job per
+    scale).  The model must not sample the scale (``args.fixed_scale``).  Returns ``lnZ[len(scales)]``."""
+    torch = _lib.torch_cuda()
+    dist = _dist() if distributed else None
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+    start, n = shard_range(count, rank, world, first_index)
+    sc = torch.as_tensor(np.ascontiguousarray(scales, dtype=np.float64)).cuda()
+    ns = int(sc.numel())
+    lse = torch.empty((ns, 2), dtype=torch.float64, device='cuda')
+    lse[:, 0] = -np.inf
+    lse[:, 1] = 0.0
+    lib = _lib.load()
+    nbytes = int(lib.gf_scan_evidence_grid_workspace(ns))
+    work = torch.empty(max(nbytes, 1), dtype=torch.uint8, device='cuda')
+    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=0)
+    _lib.check(lib.gf_scan_evidence_grid(fm.ref, C.byref(cfg), _lib.ptr(sc), ns, _lib.ptr(lse), _lib.ptr(work), nbytes, _lib.stream_ptr(torch)))
+    if dist and world > 1:
+        gmax = lse[:, 0].clone()
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
+        part = torch.where(torch.isfinite(gmax), lse[:, 1] * torch.exp(lse[:, 0] - gmax), torch.zeros_like(gmax))
+        dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        lse = torch.stack([gmax, part], dim=1)
+    h = lse.cpu().numpy()
+    with np.errstate(divide='ignore'):
+        return np.where(h[:, 1] > 0, h[:, 0] + np.log(h[:, 1]) - np.log(count), -np.inf)

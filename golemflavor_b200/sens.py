@@ -21,7 +21,7 @@ from .mcmc import DeviceEnsembleSampler, flat_seed
 from .param import Param, ParamSet
 from .scan import DEFAULT_BINNING, _dist, shard_range, sm_paramset
 
-__all__ = ['scale_grid', 'sweep_paramset', 'sweep', 'evidence_grid']
+__all__ = ['scale_grid', 'sweep_paramset', 'sweep', 'evidence_grid', 'get_limit', 'limits', 'BAYES_K']
 
 
 def scale_grid(dimension, segments):
@@ -116,36 +116,42 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
 
 
 def evidence_grid(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, source_ratio=(1, 2, 0),
-                  injected_ratio=(1, 1, 1), smearing=0.02, samples=1_000_000, seed=26, binning=DEFAULT_BINNING):
+                  injected_ratio=(1, 1, 1), smearing=0.02, samples=1_000_000, seed=26, binning=DEFAULT_BINNING, return_maxllh=False):
     """Monte-Carlo evidence per (dimension, scale) grid point (``scripts/sens.py:289-294`` stores
     ``(scale, lnZ)`` per point): the six SM nuisance parameters are drawn from their priors, the scale is
     frozen at the grid value, ``lnZ = ln mean(L)``.  Returns ``{dimension: array[segments, 2]}`` like the
-    reference's ``evidence_arr``; Bayes factors against the null point (scale -100) follow by subtraction
-    (``plot.get_limit``, ``plot.py:149-213``)."""
+    reference's ``evidence_arr`` (with ``return_maxllh`` also the ``maxllh_arr`` twin, ``sens.py:290-294``: the largest
+    ln L among the samples); Bayes factors against the null point (scale -100) and the limit follow with
+    ``get_limit`` (``plot.py:149-213``).
+
+    ONE launch per dimension (``gf_scan_evidence_grid``): every prior sample is drawn once, the scale-independent part
+    of the physics is built once, and the sample is evaluated at all scales of the grid; samples are sharded over the
+    ranks of the process group and the per-scale (max, sum-exp) pairs are merged with two all-reduces at the end."""
     import ctypes as C
     torch = _lib.torch_cuda()
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     src = np.asarray(source_ratio, dtype=np.float64)
     inj = np.asarray(injected_ratio, dtype=np.float64)
-    grid = [(int(d), float(s)) for d in dimensions for s in scale_grid(d, segments)]
-    # every grid point is one asynchronous launch into its own (max, sum-exp) slot; the model of a dimension is
-    # flattened once and only its frozen scale changes; one read-back (and one pair of all-reduces) at the end
-    lse = torch.empty((len(grid), 2), dtype=torch.float64, device='cuda')
+    dims = [int(d) for d in dimensions]
+    grids = [scale_grid(d, segments) for d in dims]
+    nsc = [len(g) for g in grids]
+    offs = np.concatenate([[0], np.cumsum(nsc)])
+    scales = torch.as_tensor(np.concatenate(grids)).cuda()
+    lse = torch.empty((int(offs[-1]), 2), dtype=torch.float64, device='cuda')
     lse[:, 0] = -np.inf
     lse[:, 1] = 0.0
     start, n = shard_range(samples, rank, world)
     cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=0)
-    lib, stream, base = _lib.load(), _lib.stream_ptr(torch), lse.data_ptr()
-    models = {}
-    for i, (dim, scale) in enumerate(grid):
-        if dim not in models:
-            args = Namespace(source_ratio=src / src.sum(), dimension=dim, texture=texture, binning=np.asarray(binning),
-                             no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing), fixed_scale=scale)
-            models[dim] = _model.flatten(args, None, ParamSet(sm_paramset(with_mass=True)))
-        fm = models[dim]
-        fm.struct.fixed_loglam = scale
-        _lib.check(lib.gf_scan_evidence(fm.ref, C.byref(cfg), C.c_void_p(base + 16 * i), stream))
+    lib, stream = _lib.load(), _lib.stream_ptr(torch)
+    work_bytes = int(lib.gf_scan_evidence_grid_workspace(max(nsc)))
+    work = _workspace(torch, work_bytes)
+    for k, dim in enumerate(dims):
+        args = Namespace(source_ratio=src / src.sum(), dimension=dim, texture=texture, binning=np.asarray(binning),
+                         no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing), fixed_scale=-100.0)
+        fm = _model.flatten(args, None, ParamSet(sm_paramset(with_mass=True)))
+        _lib.check(lib.gf_scan_evidence_grid(fm.ref, C.byref(cfg), C.c_void_p(scales.data_ptr() + 8 * int(offs[k])), nsc[k],
+                                             C.c_void_p(lse.data_ptr() + 16 * int(offs[k])), _lib.ptr(work), work_bytes, stream))
     if dist and world > 1:
         gmax = lse[:, 0].clone()
         dist.all_reduce(gmax, op=dist.ReduceOp.MAX)
@@ -155,7 +161,74 @@ def evidence_grid(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.O
     h = lse.cpu().numpy()
     with np.errstate(divide='ignore'):
         lnz = np.where(h[:, 1] > 0, h[:, 0] + np.log(h[:, 1]) - np.log(samples), -np.inf)
-    out = {}
-    for (dim, scale), z in zip(grid, lnz):
-        out.setdefault(int(dim), []).append((scale, z))
-    return {d: np.array(rows) for d, rows in out.items()}
+    allsc = np.concatenate(grids)
+    ev = {d: np.column_stack([allsc[offs[k]:offs[k + 1]], lnz[offs[k]:offs[k + 1]]]) for k, d in enumerate(dims)}
+    if return_maxllh:
+        return ev, {d: np.column_stack([allsc[offs[k]:offs[k + 1]], h[offs[k]:offs[k + 1], 0]]) for k, d in enumerate(dims)}
+    return ev
+
+
+_WORK = {}
+
+
+def _workspace(torch, nbytes):
+    """Scratch of the grid kernel, allocated once per (device, size class) and reused by later calls."""
+    key = torch.cuda.current_device()
+    buf = _WORK.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _WORK[key] = torch.empty(int(nbytes), dtype=torch.uint8, device='cuda')
+    return buf
+
+
+BAYES_K = 1.   # golemflavor/plot.py:82: "Strong degree of belief"
+
+
+def get_limit(scales, statistic, args=None, mask_initial=False, return_interp=False, bayes_k=BAYES_K, verbose=False):
+    """Limit on the new-physics scale from the evidence curve of one operator dimension (``plot.get_limit``,
+    ``plot.py:149-213``; the consumer of the ``(scale, lnZ)`` pairs ``scripts/sens.py:289-294`` stores).
+
+    ``scales[0]`` is the null point (-100), ``statistic`` = lnZ per scale.  A parametric cubic spline through
+    ``(scale, lnZ)`` (SciPy ``splprep(s=0)`` / ``splev`` on 1000 points, as the reference) gives the reduced evidence
+    ``-(lnZ - lnZ_null)``; the limit is the first splined scale where it exceeds ``ln 10^BAYES_K``, minus ``log10 2``
+    (conversion to the standard SME coefficient, ``plot.py:208-210``).  Same outcomes as the reference: ``AssertionError``
+    ('Discovered LV!') if the null point itself is disfavoured by more than the threshold, ``None`` when no splined point
+    crosses it, when the contour is peaked (>= 2 grid points beyond the crossing fall 0.1 below the threshold) or when
+    fewer than 2 grid points beyond the crossing reach it; ``return_interp`` returns ``(splined scales, reduced evidence)``."""
+    from scipy.interpolate import splev, splprep
+    scales = np.asarray(scales, dtype=np.float64)
+    statistic = np.asarray(statistic, dtype=np.float64)
+    thr = np.log(10 ** bayes_k)
+    if args is not None and getattr(args, 'stat_method', None) is not None and \
+            str(getattr(args.stat_method, 'name', args.stat_method)).upper() != 'BAYESIAN':
+        raise NotImplementedError
+    if (statistic[0] - np.max(statistic)) > thr:
+        raise AssertionError('Discovered LV!')
+    tck, _ = splprep([scales, statistic], s=0)
+    sc, st = splev(np.linspace(0, 1, 1000), tck)
+    if mask_initial:
+        keep = sc >= scales[1]
+        sc, st = sc[keep], st[keep]
+    null = statistic[np.argmin(scales)]
+    reduced_ev = -(st - null)
+    al = sc[reduced_ev > thr]
+    if len(al) == 0:
+        if verbose:
+            print('No points above the threshold')
+        return None
+    re = -(statistic - null)[scales > al[0]]
+    if np.sum(re < thr - 0.1) >= 2:
+        if verbose:
+            print('Warning, peaked contour does not exclude large scales!')
+        return None
+    if np.sum(re >= thr + 0.0) < 2:
+        if verbose:
+            print('Warning, only single point above threshold!')
+        return None
+    if return_interp:
+        return sc, reduced_ev
+    return al[0] - np.log10(2.)
+
+
+def limits(evidence, **kwargs):
+    """``get_limit`` for every dimension of an ``evidence_grid`` result: ``{dimension: limit or None}``."""
+    return {d: get_limit(ev[:, 0], ev[:, 1], **kwargs) for d, ev in evidence.items()}

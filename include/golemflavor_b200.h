@@ -201,6 +201,14 @@ int gf_ternary_hist(const double* d_fr /*[n][3]*/, int64_t n, int32_t nb, unsign
  * d_lse[0] = max ln L, d_lse[1] = sum exp(ln L - max), merged with the values already stored there
  * (initialise to {-inf, 0}); ln mean(L) = d_lse[0] + log(d_lse[1]) - log(N).  cfg->nb is unused. */
 int gf_scan_evidence(const gf_model* model, const gf_scan_config* cfg, double* d_lse /*[2]*/, void* stream);
+/* The whole scale grid of one operator dimension in ONE launch (scripts/sens.py:199-201, 232-294: `eval_scales` x one
+ * MultiNest run each): the model's scale is NOT sampled (col_scale = -1); every prior sample is drawn once and evaluated at
+ * each of the `nscales` frozen values d_scales[s] = log10(Lambda_s), and d_lse[s][0..1] accumulates (max ln L, sum exp) per
+ * scale exactly like gf_scan_evidence (initialise to {-inf, 0}; the values already there are merged).  d_work is scratch
+ * of at least gf_scan_evidence_grid_workspace(nscales) bytes (any contents; reusable by the next call on the same stream). */
+uint64_t gf_scan_evidence_grid_workspace(int32_t nscales);
+int gf_scan_evidence_grid(const gf_model* model, const gf_scan_config* cfg, const double* d_scales /*[nscales]*/, int32_t nscales,
+                          double* d_lse /*[nscales][2]*/, void* d_work, uint64_t work_bytes, void* stream);
 /* Highest-density coverage region of a histogram (plot.flavor_contour, plot.py:372-384: normalise,
  * sort cells by content, cumulative sum, `thres = searchsorted(cumsum, coverage/100)`, mask the first
  * `thres` cells).  d_mask[i] = 1 for the cells inside the region.  h_info (host, optional) receives

@@ -120,3 +120,13 @@ def cubic_w(delta):
     w = np.empty_like(d)
     load().hh_cubic_w(_p(d), C.c_int64(d.size), _p(w))
     return w
+
+
+def fr_scales(fm, theta, scales):
+    """gf_point_fr_scales: compositions [n, ns, 3] of every point at each frozen scale, + status bytes."""
+    th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
+    sc = np.ascontiguousarray(scales, dtype=np.float64)
+    n, ns = th.shape[0], sc.shape[0]
+    out, st = np.empty((n, ns, 3)), np.empty((n, ns), dtype=np.uint8)
+    _lib.check(load().hh_fr_scales(fm.ref, _p(th), C.c_int64(n), _p(sc), C.c_int(ns), _p(out), _p(st)))
+    return out, st

@@ -140,3 +140,28 @@ extern "C" int hh_ensemble(const gf_model* model, const gf_ensemble_config* cfg,
 extern "C" void hh_cubic_w(const double* delta, int64_t n, double* w) {
     for (int64_t i = 0; i < n; ++i) w[i] = gfp_cubic_w(delta[i]);
 }
+
+/* the multi-scale evaluation of the evidence grid: fr[n][ns][3] at logLam = scales[s] for every point (the model's own
+ * scale column / fixed_loglam is ignored) */
+extern "C" int hh_fr_scales(const gf_model* model, const double* theta, int64_t n, const double* scales, int ns, double* fr, uint8_t* st) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    const bool fixed = gf_model_is_fixed_spec(d);
+    for (int64_t i = 0; i < n; ++i) {
+        auto get = [&](int k) { return theta[i * d.ndim + k]; };
+        gf_point q;
+        auto lam_of = [&](int s) { return pow(10.0, scales[s]); };
+        auto emit = [&](int s, const double* f, unsigned status) {
+            memcpy(fr + 3 * (i * ns + s), f, 3 * sizeof(double));
+            if (st) st[i * ns + s] = (uint8_t)status;
+        };
+        if (fixed) {
+            gf_resolve_point<GF_SPEC_FIXED>(d, get, q);
+            gf_point_fr_scales<GF_SPEC_FIXED, 2>(d, q, ns, lam_of, emit);
+        } else {
+            gf_resolve_point<GF_SPEC_GENERIC>(d, get, q);
+            gf_point_fr_scales<GF_SPEC_GENERIC, 1>(d, q, ns, lam_of, emit);
+        }
+    }
+    return 0;
+}

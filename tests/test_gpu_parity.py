@@ -1103,6 +1103,61 @@ def test_scan_evidence_against_oracle(torch):
     assert ev[3].shape == (4, 2) and ev[3][0, 0] == -100 and abs(ev[3][0, 1] - ev[6][0, 1]) < 1e-9
 
 
+def test_evidence_grid_kernel_against_per_scale_launches_and_oracle(torch):
+    """gf_scan_evidence_grid (one launch per dimension: every prior sample evaluated at all frozen scales) against
+    (i) gf_scan_evidence launched once per scale on the same Philox draws and (ii) the oracle's likelihood on those
+    draws; sample-shard invariance; the generic (sampled-source) specialisation; then the limit extraction on top."""
+    from argparse import Namespace
+    from golemflavor_b200 import sens
+    from golemflavor_b200.param import ParamSet
+    lib = _lib.load()
+    n = 30000
+    for dim, nsc in ((6, 23), (3, 7)):
+        scales = sens.scale_grid(dim, nsc)
+        args = Namespace(source_ratio=np.array([1, 2, 0.]) / 3, dimension=dim, texture=Texture.OET, binning=models.BINNING, no_bsm=False,
+                         injected_ratio=[1 / 3, 1 / 3, 1 / 3], smearing=0.02, fixed_scale=-100.0)
+        fm = model.flatten(args, None, ParamSet(scan.sm_paramset(with_mass=True)))
+        before = lib.gf_launch_count()
+        got = scan.scan_evidence_grid(fm, scales, n, seed=26, distributed=False)
+        assert lib.gf_launch_count() - before == 1
+        theta, _, _ = scan.scan_samples(fm, n, seed=26)
+        for k, sc in enumerate(scales):
+            fm.struct.fixed_loglam = float(sc)
+            one = scan.scan_evidence(fm, n, seed=26, distributed=False)
+            assert abs(got[k] - one) <= 1e-12 * abs(one), (dim, sc, got[k], one)
+            if k in (0, 1, nsc // 2, nsc - 1):
+                ref_fr = truth.eigh_flux_averaged_fr(theta[:, :4], theta[:, 4:6], model.TEXTURE_ANGLES['OET'], np.full(n, sc), dim,
+                                                     models.BINNING, args.source_ratio)
+                ll = go.batch_multi_gaussian(ref_fr, [1 / 3, 1 / 3, 1 / 3], 0.02)
+                fin = np.isfinite(ll)
+                mx = ll[fin].max()
+                ref = mx + np.log(np.exp(ll[fin] - mx).sum()) - np.log(n)
+                assert abs(got[k] - ref) < 1e-9 * abs(ref), (dim, sc, got[k], ref)
+        parts = [scan.scan_evidence_grid(fm, scales, c, seed=26, first_index=s, distributed=False) + np.log(c) for s, c in ((0, 11000), (11000, 19000))]
+        assert np.max(np.abs(np.logaddexp(parts[0], parts[1]) - np.log(n) - got) / np.abs(got)) < 1e-12
+    # sampled source (GENERIC specialisation, column-map path) + a model with a sampled scale is refused
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_llh.npz'))
+    a9, as9, ps9 = models.bsm_sampled_source(g['asimov_angles'], 'angles', 6, Texture.OUT)
+    with pytest.raises(ValueError):
+        scan.scan_evidence_grid(model.flatten(a9, as9, ps9), [-40.0], 100, distributed=False)
+    a9.fixed_scale = -100.0
+    fm8 = model.flatten(a9, as9, ParamSet([p for p in ps9 if p.name != 'logLam']))
+    sc8 = np.array([-100.0, -44.0, -38.5, -33.0])
+    got8 = scan.scan_evidence_grid(fm8, sc8, 8000, seed=3, distributed=False)
+    for k, sc in enumerate(sc8):
+        fm8.struct.fixed_loglam = float(sc)
+        one = scan.scan_evidence(fm8, 8000, seed=3, distributed=False)
+        assert abs(got8[k] - one) <= 1e-12 * abs(one)
+    # the full grid through sens.evidence_grid and the limit extraction of plot.py:149-213 on top
+    ev, mx = sens.evidence_grid(dimensions=(3, 6), segments=20, samples=50000, injected_ratio=(1, 1, 1), return_maxllh=True)
+    assert ev[3].shape == (20, 2) and ev[3][0, 0] == -100 and abs(ev[3][0, 1] - ev[6][0, 1]) < 1e-9
+    assert np.all(mx[6][:, 1] >= ev[6][:, 1]) and np.array_equal(mx[6][:, 0], ev[6][:, 0])
+    lim = sens.limits(ev)
+    for d in (3, 6):   # an injected (1:1:1) composition is compatible with the null: large scales are excluded
+        lo, hi = model.SCALE_BOUNDARIES[d]
+        assert lim[d] is not None and lo - 1 < lim[d] < hi, (d, lim[d])
+
+
 def test_cli_scan_outputs(torch, tmp_path):
     from golemflavor_b200 import cli
     out = cli.main(['mc_unitary', '--nwalkers', '20', '--nsteps', '50', '--datadir', str(tmp_path)])

@@ -537,3 +537,25 @@ def test_mcmc_driver_probes_scalar_callables(capsys):
     capsys.readouterr()
     assert s1.shape == s2.shape == (80, 2) and np.allclose(s1, s2)
     assert calls['scalar'] > 8 * 15 and calls['batch'] < 2 * 15 + 5
+
+
+def test_get_limit_matches_reference_fixture(golden):
+    """sens.get_limit against plot.get_limit of the unmodified reference (tests/golden/make_golden_limit.py): the same
+    limit / None outcome and the same splined reduced-evidence curve on every fixture curve."""
+    from golemflavor_b200 import sens
+    g = golden('ref_limit.npz')
+    assert float(g['bayes_k']) == sens.BAYES_K
+    nlim = 0
+    for k in range(int(g['n'])):
+        sc, st, ref, mi = g['scales_%d' % k], g['stat_%d' % k], float(g['limit_%d' % k]), bool(g['mask_%d' % k])
+        got = sens.get_limit(sc, st, mask_initial=mi)
+        if np.isnan(ref):
+            assert got is None, (k, got)
+            continue
+        nlim += 1
+        assert got is not None and abs(got - ref) < 1e-12, (k, got, ref)
+        isc, iev = sens.get_limit(sc, st, mask_initial=mi, return_interp=True)
+        assert np.allclose(isc, g['interp_sc_%d' % k], rtol=0, atol=1e-12) and np.allclose(iev, g['interp_ev_%d' % k], rtol=0, atol=1e-10)
+    assert nlim >= 10
+    ev = {6: np.column_stack([g['scales_0'], g['stat_0']])}
+    assert sens.limits(ev)[6] == sens.get_limit(g['scales_0'], g['stat_0'])
