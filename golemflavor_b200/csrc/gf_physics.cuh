@@ -264,15 +264,17 @@ struct gfp_x4 {
 };
 
 /*
- * Closed-form |V_ai|^2 from the invariants of a TRACE-FREE Hermitian 3x3 matrix: diagonal
- * e0,e1,e2, squared moduli a2 = |H01|^2, b2 = |H02|^2, c2 = |H12|^2, Q = tr(H^2)/6 and det H.
- * Eigenvalues 2 sqrt(Q) cos((phi + 2 pi k)/3) with cos(phi) = det / (2 Q^(3/2)); squared
- * eigenvector moduli from the eigenvector-eigenvalue identity |V_ai|^2 p'(l_i) = det(l_i - M_a)
- * (M_a = 2x2 principal minor).  Returns false -- out not written -- when the closest eigenvalue
- * pair is nearer than the fast-path limit or the input is degenerate / non-finite; the caller then
- * runs the Jacobi fallback.
+ * Closed-form |V_ai|^2 from the invariants of a TRACE-FREE Hermitian 3x3 matrix: diagonal entries e0, e1, the
+ * diagonal COFACTORS k0 = e1 e2 - |H12|^2, k1 = e0 e2 - |H02|^2, Q = tr(H^2)/6 and det H.
+ * Eigenvalues 2 sqrt(Q) cos((phi + 2 pi k)/3) with cos(phi) = det / (2 Q^(3/2)); squared eigenvector moduli from
+ * the eigenvector-eigenvalue identity |V_ai|^2 p'(l_i) = det(l_i - M_a) (M_a = 2x2 principal minor).  With
+ * e0 + e1 + e2 = 0 the minor determinants are (l - e1)(l - e2) - |H12|^2 = l (l + e0) + k0 and
+ * (l - e0)(l - e2) - |H02|^2 = l (l + e1) + k1: one addition and one FMA each, and neither e2 nor the squared
+ * off-diagonal moduli are needed per matrix.  Returns false -- the caller then discards `out` -- when the closest
+ * eigenvalue pair is nearer than the fast-path limit or the input is degenerate / non-finite; the caller then
+ * runs the deflation fallback.
  */
-GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, double c2, double Q, double hdet, gfp_x4& out) {
+GF_HD bool gfp_eig_core(double e0, double e1, double k0, double k1, double Q, double hdet, gfp_x4& out) {
     /* hdet = det / 2.  Straight-line code on purpose (no early exit): the caller evaluates two energy
      * bins back to back and the compiler interleaves their independent dependency chains -- with 16
      * resident warps per SM the kernels are bound by the latency of this chain.  Degenerate or
@@ -286,11 +288,11 @@ GF_HD bool gfp_eig_core(double e0, double e1, double e2, double a2, double b2, d
     const double l0 = copysign(sq - sq * w, r);         /* 2 sqrt(Q) cos(phi/3), isolated eigenvalue */
     const double half_gap = (0.8660254037844386 * sq) * (s2 * gfp_rsqrt(s2));
     const double l1 = fma(-0.5, l0, half_gap);
-    /* eigenvector-eigenvalue identity |V_ai|^2 p'(l_i) = det(l_i - M_a) for rows a = 0, 1; for the
-     * trace-free cubic p'(l) = 3 (l^2 - Q): no third minor, and the operands stay register-light
-     * (a DFMA reading three distinct register pairs issues at 2/3 rate on B200) */
-    const double n00 = fma(l0 - e1, l0 - e2, -c2), n10 = fma(l0 - e0, l0 - e2, -b2);
-    const double n01 = fma(l1 - e1, l1 - e2, -c2), n11 = fma(l1 - e0, l1 - e2, -b2);
+    /* eigenvector-eigenvalue identity for rows a = 0, 1; for the trace-free cubic p'(l) = 3 (l^2 - Q): no third
+     * minor, and the operands stay register-light (a DFMA reading three distinct register pairs issues at 2/3
+     * rate on B200) */
+    const double n00 = fma(l0, l0 + e0, k0), n10 = fma(l0, l0 + e1, k1);
+    const double n01 = fma(l1, l1 + e0, k0), n11 = fma(l1, l1 + e1, k1);
     const double p0 = fma(l0, l0, -Q), p1 = fma(l1, l1, -Q); /* p'(l_i) / 3 */
     const double q = gfp_rcp(3.0 * (p0 * p1));
     const double i0 = q * p1, i1 = q * p0;
@@ -322,25 +324,26 @@ GF_HD bool gfp_herm3_x4_fast(const gfp_herm3& h, gfp_x4& out) {
     const double aci = fma(h.ar, h.ci, h.ai * h.cr);
     const double tri = fma(acr, h.br, aci * h.bi);
     const double det = fma(2.0, tri, e0 * e1 * e2) - fma(e0, c2, fma(e1, b2, e2 * a2));
-    return gfp_eig_core(e0, e1, e2, a2, b2, c2, p2 * (1.0 / 6.0), 0.5 * det, out);
+    return gfp_eig_core(e0, e1, fma(e1, e2, -c2), fma(e0, e2, -b2), p2 * (1.0 / 6.0), 0.5 * det, out);
 }
 
 /*
  * The matrix pencil H(rho) = H0 + rho T of the energy-bin loop (fr.py:441-452: only the scalar
  * rho = 10^logLam * 2 E^(d-2) changes from bin to bin).  Every invariant gfp_eig_core needs is a
- * polynomial in rho, so a bin costs 14 FMAs for the invariants instead of rebuilding the matrix and
+ * polynomial in rho -- the trace-free diagonal (degree 1), the diagonal cofactors and Q (degree 2), the
+ * determinant (degree 3) -- so a bin costs 11 FMAs for the invariants instead of rebuilding the matrix and
  * its determinant.  The coefficients split into a part that depends on T alone (gfp_pencil_T: a
  * model constant for the fixed textures, then read straight from the constant bank) and a per-point
  * part (gfp_pencil_P).
  */
 struct gfp_pencil_T {
-    double te[3];        /* trace-free diagonal of T                          */
-    double a22, b22, c22; /* |T01|^2, |T02|^2, |T12|^2                         */
-    double q2, d3;       /* tr(T'^2)/6, det(T')/2                             */
+    double te[3];        /* trace-free diagonal of T                                              */
+    double kt0, kt1;     /* diagonal cofactors of T': te1 te2 - |T12|^2, te0 te2 - |T02|^2         */
+    double q2, d3;       /* tr(T'^2)/6, det(T')/2                                                 */
 };
 struct gfp_pencil_P {
-    double e[3];                 /* trace-free diagonal of H0: e_k(rho) = e[k] + rho te[k]            */
-    double a2[2], b2[2], c2[2];  /* |H01|^2(rho) = a2[0] + rho (a2[1] + rho a22), ...                  */
+    double e[2];                 /* trace-free diagonal of H0: e_k(rho) = e[k] + rho te[k], k = 0, 1   */
+    double k0[2], k1[2];         /* cofactors: k_a(rho) = k_a[0] + rho (k_a[1] + rho kt_a)             */
     double q[2];                 /* Q(rho) = q[0] + rho (q[1] + rho q2)                                */
     double d[3];                 /* det(rho)/2 = d[0] + rho (d[1] + rho (d[2] + rho d3))               */
 };
@@ -391,9 +394,8 @@ GF_HD gfp_pencil_T gfp_make_pencil_T(const gfp_herm3& T) {
     gfp_pencil_T t;
     const double mut = (T.d0 + T.d1 + T.d2) * (1.0 / 3.0);
     t.te[0] = T.d0 - mut; t.te[1] = T.d1 - mut; t.te[2] = T.d2 - mut;
-    t.a22 = fma(T.ar, T.ar, T.ai * T.ai);
-    t.b22 = fma(T.br, T.br, T.bi * T.bi);
-    t.c22 = fma(T.cr, T.cr, T.ci * T.ci);
+    t.kt0 = fma(t.te[1], t.te[2], -fma(T.cr, T.cr, T.ci * T.ci));
+    t.kt1 = fma(t.te[0], t.te[2], -fma(T.br, T.br, T.bi * T.bi));
     gfp_spectrum_invariants(GFP_T_EIG1, GFP_T_EIG2, t.q2, t.d3);
     return t;
 }
@@ -403,25 +405,31 @@ GF_HD gfp_pencil_T gfp_make_pencil_T(const gfp_herm3& T) {
 GF_HD gfp_pencil_P gfp_make_pencil_P(const gfp_herm3& h0, double m1, double m2, const gfp_herm3& T, const double* te, const gfp_adj3& adjT) {
     gfp_pencil_P p;
     const double mu0 = (h0.d0 + h0.d1 + h0.d2) * (1.0 / 3.0);
-    p.e[0] = h0.d0 - mu0; p.e[1] = h0.d1 - mu0; p.e[2] = h0.d2 - mu0;
-    p.a2[0] = fma(h0.ar, h0.ar, h0.ai * h0.ai); p.a2[1] = 2.0 * fma(h0.ar, T.ar, h0.ai * T.ai);
-    p.b2[0] = fma(h0.br, h0.br, h0.bi * h0.bi); p.b2[1] = 2.0 * fma(h0.br, T.br, h0.bi * T.bi);
-    p.c2[0] = fma(h0.cr, h0.cr, h0.ci * h0.ci); p.c2[1] = 2.0 * fma(h0.cr, T.cr, h0.ci * T.ci);
+    const double pe[3] = {h0.d0 - mu0, h0.d1 - mu0, h0.d2 - mu0};
+    p.e[0] = pe[0]; p.e[1] = pe[1];
+    /* rho-linear coefficients of |H01|^2, |H02|^2, |H12|^2: 2 Re(H0_ab conj(T_ab)) */
+    const double a21 = 2.0 * fma(h0.ar, T.ar, h0.ai * T.ai);
+    const double b21 = 2.0 * fma(h0.br, T.br, h0.bi * T.bi);
+    const double c21 = 2.0 * fma(h0.cr, T.cr, h0.ci * T.ci);
+    const gfp_adj3 adjH = gfp_adj_tf(pe, h0);
+    /* diagonal cofactors e1 e2 - |H12|^2 and e0 e2 - |H02|^2 of H0' + rho T': the constant terms are those of adj(H0'),
+     * the rho^2 terms those of adj(T') (gfp_pencil_T / the model constant adjT) */
+    p.k0[0] = adjH.k0; p.k0[1] = fma(pe[1], te[2], fma(pe[2], te[1], -c21));
+    p.k1[0] = adjH.k1; p.k1[1] = fma(pe[0], te[2], fma(pe[2], te[0], -b21));
     gfp_spectrum_invariants(m1, m2, p.q[0], p.d[0]);
-    p.q[1] = (1.0 / 6.0) * fma(2.0, p.a2[1] + p.b2[1] + p.c2[1], 2.0 * fma(p.e[0], te[0], fma(p.e[1], te[1], p.e[2] * te[2])));
-    p.d[1] = 0.5 * gfp_tr_adj(p.e, h0, te, T);
-    p.d[2] = 0.5 * gfp_tr_adj_pre(adjT, p.e, h0);
+    p.q[1] = (1.0 / 6.0) * fma(2.0, a21 + b21 + c21, 2.0 * fma(pe[0], te[0], fma(pe[1], te[1], pe[2] * te[2])));
+    p.d[1] = 0.5 * gfp_tr_adj_pre(adjH, te, T);
+    p.d[2] = 0.5 * gfp_tr_adj_pre(adjT, pe, h0);
     return p;
 }
 
 GF_HD bool gfp_pencil_x4_fast(const gfp_pencil_P& p, const gfp_pencil_T& t, double rho, gfp_x4& out) {
-    const double e0 = fma(rho, t.te[0], p.e[0]), e1 = fma(rho, t.te[1], p.e[1]), e2 = fma(rho, t.te[2], p.e[2]);
-    const double a2 = fma(fma(t.a22, rho, p.a2[1]), rho, p.a2[0]);
-    const double b2 = fma(fma(t.b22, rho, p.b2[1]), rho, p.b2[0]);
-    const double c2 = fma(fma(t.c22, rho, p.c2[1]), rho, p.c2[0]);
+    const double e0 = fma(rho, t.te[0], p.e[0]), e1 = fma(rho, t.te[1], p.e[1]);
+    const double k0 = fma(fma(t.kt0, rho, p.k0[1]), rho, p.k0[0]);
+    const double k1 = fma(fma(t.kt1, rho, p.k1[1]), rho, p.k1[0]);
     const double Q = fma(fma(t.q2, rho, p.q[1]), rho, p.q[0]);
     const double hdet = fma(fma(fma(t.d3, rho, p.d[2]), rho, p.d[1]), rho, p.d[0]);
-    return gfp_eig_core(e0, e1, e2, a2, b2, c2, Q, hdet, out);
+    return gfp_eig_core(e0, e1, k0, k1, Q, hdet, out);
 }
 
 /*

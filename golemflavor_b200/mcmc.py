@@ -325,8 +325,8 @@ def mcmc(p0, ln_prob, ndim, nwalkers, burnin, nsteps, threads=1, vectorize=None,
             print('device sampler seed', seed)
         sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, seed=seed)
     else:
-        if vectorize is None:
-            vectorize = _accepts_batches(ln_prob, np.asarray(p0, dtype=np.float64))
+        if vectorize is None:   # the package's own callables are batched; foreign ones are probed once
+            vectorize = True if _as_lnprob_object(ln_prob) is not None else _accepts_batches(ln_prob, np.asarray(p0, dtype=np.float64))
         sampler = EnsembleSampler(nwalkers, ndim, ln_prob, threads=threads, vectorize=vectorize, seed=seed)
     print("Running burn-in")
     pos = np.asarray(p0)
