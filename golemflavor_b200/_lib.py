@@ -134,6 +134,29 @@ def load():
     return _lib
 
 
+TORCH_OPS_PATH = os.path.join(LIB_DIR, 'libgolemflavor_b200_torch.so')
+TORCH_OPS = ('abi_version', 'lnprob', 'lnprior', 'flux_averaged_fr', 'angles_to_u', 'angles_to_fr', 'u_to_fr', 'multi_gaussian', 'scan_hist')
+_ops = None
+
+
+def torch_ops():
+    """``torch.ops.golemflavor``: the C ABI registered as torch operators (csrc/gf_torch_ops.cpp -- tensors in, tensors
+    out, torch's current stream), loaded once with ``torch.ops.load_library``.  Raises if it has not been built."""
+    global _ops
+    if _ops is None:
+        import torch
+        load()   # the C-ABI library first: same checks, and the operator library links against it
+        if not os.path.exists(TORCH_OPS_PATH):
+            raise GolemFlavorError('golemflavor_b200: {0} is missing -- build it first (python -m golemflavor_b200.build); '
+                                   'there is no fallback'.format(TORCH_OPS_PATH))
+        torch.ops.load_library(TORCH_OPS_PATH)
+        ops = torch.ops.golemflavor
+        if int(ops.abi_version()) != 1:
+            raise GolemFlavorError('golemflavor_b200: ABI version mismatch between the operator library and _lib.py')
+        _ops = ops
+    return _ops
+
+
 def check(rc):
     """Map a C return code onto the reference's exception conventions
     (bad arguments -> ValueError, as ``fr.py:198-202``; runtime -> GolemFlavorError)."""

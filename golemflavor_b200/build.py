@@ -26,6 +26,32 @@ def nvcc_path():
     raise RuntimeError('nvcc not found (set NVCC=/path/to/nvcc)')
 
 
+TORCH_OPS_SRC = os.path.join(CSRC, 'gf_torch_ops.cpp')
+TORCH_OPS_PATH = os.path.join(LIB_DIR, 'libgolemflavor_b200_torch.so')
+
+
+def build_torch_ops(force=False, verbose=False):
+    """Compile the `torch.ops.golemflavor.*` registration (gf_torch_ops.cpp) with g++ against the torch headers of the
+    running interpreter, linked to the C-ABI library next to it (rpath $ORIGIN).  In-tree, no JIT cache."""
+    deps = [TORCH_OPS_SRC, os.path.join(CSRC, '..', '..', 'include', 'golemflavor_b200.h')]
+    if not force and os.path.exists(TORCH_OPS_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(TORCH_OPS_PATH) for d in deps):
+        return TORCH_OPS_PATH
+    build_library()
+    import torch
+    tdir = os.path.dirname(torch.__file__)
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(nvcc_path())), 'include')
+    cmd = ['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-D_GLIBCXX_USE_CXX11_ABI=%d' % int(torch._C._GLIBCXX_USE_CXX11_ABI),
+           '-I' + os.path.join(tdir, 'include'), '-I' + os.path.join(tdir, 'include', 'torch', 'csrc', 'api', 'include'), '-I' + cuda_inc,
+           TORCH_OPS_SRC, '-o', TORCH_OPS_PATH, '-L' + LIB_DIR, '-lgolemflavor_b200', '-L' + os.path.join(tdir, 'lib'),
+           '-ltorch', '-ltorch_cpu', '-ltorch_cuda', '-lc10', '-lc10_cuda', '-Wl,-rpath,$ORIGIN', '-Wl,-rpath,' + os.path.join(tdir, 'lib')]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError('g++ failed ({0}): {1}'.format(res.returncode, ' '.join(cmd)))
+    return TORCH_OPS_PATH
+
+
 def is_stale():
     if not os.path.exists(LIB_PATH):
         return True
@@ -51,3 +77,4 @@ def build_library(force=False, verbose=False):
 
 if __name__ == '__main__':
     print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_torch_ops(force='--force' in sys.argv, verbose='-v' in sys.argv))

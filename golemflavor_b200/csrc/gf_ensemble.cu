@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                     acc0 += h ? 0u : 1u;
                     acc1 += h ? 1u : 0u;
                 }
+                GF_STAGE(11);
                 GF_TICK(t_eval)
             }
             cluster.barrier_arrive();
@@ -220,13 +221,20 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 }
             }
             cluster.barrier_wait();
+            GF_STAGE(12);
             GF_TICK(t_sync)
         }
     }
 #ifdef GF_ENS_PROFILE
     if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
         printf("cluster sampler profile (cycles per half-step, thread 0): draws %.0f  move %.0f  barrier %.0f\n",
                (double)t_draw / (2.0 * A.nsteps), (double)t_eval / (2.0 * A.nsteps), (double)t_sync / (2.0 * A.nsteps));
+        const char* names[13] = {"(from barrier)", "partner+own loads", "stretch", "lnprior", "trig (7 sqrt + sincos)", "cols + H0", "exp10", "pencil_P",
+                                 "bin loop", "mix tail + llh", "accept test", "write-back", "arrive + draws + wait"};
+        for (int i = 0; i < 13; ++i) printf("   stage %2d %-24s %8.0f\n", i, names[i], (double)gf_stage_acc[i] / (2.0 * A.nsteps));
+        for (int i = 0; i < 16; ++i) gf_stage_acc[i] = 0;
+    }
 #endif
     if (active) {
 #pragma unroll 1

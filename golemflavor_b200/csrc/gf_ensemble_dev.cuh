@@ -88,6 +88,7 @@ GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw&
                        double* q, double& lnew) {
     const int ndim = m.ndim;
     double cv[GF_MAX_DIM], pv[GF_MAX_DIM];
+    GF_STAGE(0);
 #pragma unroll
     for (int d = 0; d < GF_MAX_DIM; ++d) {
         if (d < ndim) {
@@ -96,13 +97,16 @@ GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw&
         }
     }
     if (!FINISHED) gf_ens_finish_draw(A, dr);
+    GF_STAGE(1);
 #pragma unroll
     for (int d = 0; d < GF_MAX_DIM; ++d)
         if (d < ndim) q[d] = gf_ens_stretch(cv[d], pv[d], dr.z);
+    GF_STAGE(2);
     double fr[3];
     unsigned st = 0u;
     lnew = gf_point_lnprob<SPEC, ILP>(m, [&](int d) { return q[d]; }, fr, st);
     const double diff = dr.lz + lnew - lold;
+    GF_STAGE(10);
     return diff > dr.lu;
 }
 

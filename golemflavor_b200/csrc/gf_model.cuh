@@ -267,20 +267,25 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
         fr[2] = f[2] * inv;
     } else if (!GF_SPEC_IS_SM(SPEC)) {
         const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
+        GF_STAGE(4);
         const gfp_cols12 u = gfp_cols_from_trig(t);
         /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
          * the polynomial invariants of the pencil H0 + rho T */
         const double m1 = q.mass[0] * GFP_MASS_SCALE, m2 = q.mass[1] * GFP_MASS_SCALE;
         gfp_herm3 h0 = gfp_herm_from_cols(u, m1, m2);
+        GF_STAGE(5);
 #ifdef __CUDA_ARCH__
         const double lam = exp10(q.loglam);
 #else
         const double lam = pow(10.0, q.loglam);
 #endif
+        GF_STAGE(6);
         if (GF_SPEC_IS_FIXED(SPEC)) {
             gfp_herm3 T = m.T;
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
+            GF_STAGE(7);
             st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            GF_STAGE(8);
         } else {
             gfp_herm3 T;
             if (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) {
@@ -437,6 +442,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
     const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC)>(m, get);
+    GF_STAGE(3);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
         fr[0] = fr[1] = fr[2] = NAN;
         st = (lp != lp) ? (GFP_ST_NON_FINITE | GFP_ST_OUT_OF_PRIOR) : GFP_ST_OUT_OF_PRIOR;
@@ -447,7 +453,9 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
     st = gf_point_fr<SPEC, ILP>(m, q, fr);
     /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
     if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
-    return lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
+    const double out = lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
+    GF_STAGE(9);
+    return out;
 }
 
 #endif /* GF_MODEL_CUH */

@@ -35,6 +35,25 @@
 #define GF_HD_NOINLINE inline
 #endif
 
+/* Developer build only (-DGF_ENS_PROFILE): clock64 stage probes of the sampler's critical path, accumulated by thread 0
+ * of block 0 and printed by the cluster kernel.  Compiles to nothing otherwise. */
+#if defined(GF_ENS_PROFILE) && defined(__CUDACC__)
+static __device__ long long gf_stage_acc[16];
+static __device__ long long gf_stage_last;
+#endif
+#if defined(GF_ENS_PROFILE) && defined(__CUDA_ARCH__)
+#define GF_STAGE(i)                                       \
+    do {                                                  \
+        if (threadIdx.x == 0 && blockIdx.x == 0) {        \
+            const long long n_ = clock64();               \
+            gf_stage_acc[i] += n_ - gf_stage_last;        \
+            gf_stage_last = n_;                           \
+        }                                                 \
+    } while (0)
+#else
+#define GF_STAGE(i)
+#endif
+
 /* status bits -- must equal GF_ST_* of include/golemflavor_b200.h */
 #define GFP_ST_OUT_OF_PRIOR 1u
 #define GFP_ST_NON_UNITARY 2u

@@ -277,10 +277,7 @@ def flux_averaged_BSMu(theta, args, spectral_index, llh_paramset):
     last = th2[-1].cpu().numpy()
     for k, p in enumerate(llh_paramset):
         p.value = float(last[k])
-    out = torch.empty((n, 3), dtype=torch.float64, device='cuda')
-    st = torch.empty((n,), dtype=torch.uint8, device='cuda')
-    _lib.check(_lib.load().gf_flux_averaged_fr(fm.ref, _lib.ptr(th2), n, fm.ndim, 1, _lib.ptr(out), _lib.ptr(st),
-                                               _lib.stream_ptr(torch)))
+    out, st = _lib.torch_ops().flux_averaged_fr(th2, fm.blob)
     bad = st & (_lib.ST_NON_UNITARY | _lib.ST_NON_FINITE)
     if bool(bad.any()):
         raise AssertionError('Matrix is not unitary! ({0} of {1} points)'.format(int(bad.ne(0).sum()), n))

@@ -104,12 +104,8 @@ class LnProb(object):
         """theta [N, ndim] (NumPy or CUDA tensor) -> lnprob [N] (+ fr [N, 3], status [N]) as CUDA tensors."""
         torch = _lib.torch_cuda()
         th = _lib.to_device(theta, torch, self.ndim).reshape(-1, self.ndim)
-        n = th.shape[0]
-        out = torch.empty((n,), dtype=torch.float64, device='cuda')
-        fr = torch.empty((n, 3), dtype=torch.float64, device='cuda') if want_fr else None
-        st = torch.empty((n,), dtype=torch.uint8, device='cuda') if want_status else None
-        _lib.check(_lib.load().gf_lnprob(self.model.ref, _lib.ptr(th), n, self.ndim, 1, _lib.ptr(out), _lib.ptr(fr),
-                                         _lib.ptr(st), _lib.stream_ptr(torch)))
+        # one operator call: torch.ops.golemflavor.lnprob -> gf_lnprob on torch's current stream
+        out, fr, st = _lib.torch_ops().lnprob(th, self.model.blob, bool(want_fr), bool(want_status))
         res = (out,) + ((fr,) if want_fr else ()) + ((st,) if want_status else ())
         return res if len(res) > 1 else out
 
@@ -153,8 +149,7 @@ def lnprior(theta, paramset):
     batched = th.ndim > 1
     th2 = th.reshape(-1, fm.ndim)
     _store_values(th2, paramset)
-    out = torch.empty((th2.shape[0],), dtype=torch.float64, device='cuda')
-    _lib.check(_lib.load().gf_lnprior(fm.ref, _lib.ptr(th2), th2.shape[0], fm.ndim, 1, _lib.ptr(out), _lib.stream_ptr(torch)))
+    out = _lib.torch_ops().lnprior(th2, fm.blob)
     if _is_tensor(theta):
         return out if batched else out[0]
     out = out.cpu().numpy()

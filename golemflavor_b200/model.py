@@ -51,6 +51,7 @@ class FlatModel(object):
     def __init__(self, struct, names=()):
         self.struct = struct
         self.names = tuple(names)
+        self._blob = None
         _lib.check(_lib.load().gf_model_check(self.ref))
 
     @property
@@ -61,6 +62,17 @@ class FlatModel(object):
     @property
     def ndim(self):
         return int(self.struct.ndim)
+
+    @property
+    def blob(self):
+        """The struct's bytes as a CPU uint8 tensor (shares memory with ``struct``): the form in which the model is
+        handed to the ``torch.ops.golemflavor.*`` operators."""
+        if self._blob is None:
+            import ctypes
+
+            import torch
+            self._blob = torch.frombuffer((ctypes.c_uint8 * ctypes.sizeof(self.struct)).from_buffer(self.struct), dtype=torch.uint8)
+        return self._blob
 
 
 def _new_struct():

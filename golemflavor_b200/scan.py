@@ -133,8 +133,7 @@ def scan_histogram(fm, count, nb=25, seed=26, first_index=0, distributed=True, o
     cells = (nb + 1) ** 3
     hist = out if out is not None else torch.zeros((cells,), dtype=torch.int64, device='cuda')
     kept = torch.zeros((1,), dtype=torch.int64, device='cuda')
-    cfg = _lib.ScanConfig(seed=int(seed), first_index=int(start), count=int(n), nb=int(nb))
-    _lib.check(_lib.load().gf_scan_hist(fm.ref, C.byref(cfg), _lib.ptr(hist), _lib.ptr(kept), _lib.stream_ptr(torch)))
+    _lib.torch_ops().scan_hist(fm.blob, int(seed), int(start), int(n), int(nb), hist, kept)
     if dist and world > 1:
         allreduce_counts(hist, kept)
     h = hist.reshape(nb + 1, nb + 1, nb + 1)
