@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
     k_ensemble_cluster(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
     extern __shared__ double sh_ens[];
     cg::cluster_group cluster = cg::this_cluster();
-    const int T = (int)blockDim.x, ndim = m.ndim, half = A.nwalkers / 2;
+    constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC); /* compile-time layouts: constant dimension count */
+    const int T = (int)blockDim.x, ndim = ND > 0 ? ND : m.ndim, half = A.nwalkers / 2;
     const int nc = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int64_t c = blockIdx.x / nc;
     const int wl = (int)threadIdx.x, w = rank * T + wl;
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 double q[GF_MAX_DIM];
                 double lnew;
                 if (gf_ens_move<SPEC, ILP, true>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; }, lnp_s[h * T + wl], q, lnew)) {
-                    _Pragma("unroll") for (int d = 0; d < GF_MAX_DIM; ++d)
+                    _Pragma("unroll") for (int d = 0; d < (ND > 0 ? ND : GF_MAX_DIM); ++d)
                         if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
                     lnp_s[h * T + wl] = lnew;
                     acc0 += h ? 0u : 1u;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                     if (stored < nstore) { /* running output pointers: no 64-bit index arithmetic per store */
                         if (A.chain) {
 #pragma unroll
-                            for (int d = 0; d < GF_MAX_DIM; ++d) {
+                            for (int d = 0; d < (ND > 0 ? ND : GF_MAX_DIM); ++d) {
                                 if (d < ndim) {
                                     out0[d] = pos_s[wl * ndim + d];
                                     out1[d] = pos_s[(T + wl) * ndim + d];

@@ -86,11 +86,13 @@ GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(c
 template <int SPEC, int ILP, bool FINISHED, class LoadPartner, class LoadOwn>
 GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw& dr, LoadPartner partner, LoadOwn own, double lold,
                        double* q, double& lnew) {
-    const int ndim = m.ndim;
+    /* with a compile-time layout the dimension count is a constant: no guarded work on the 16 - ndim unused slots */
+    constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC);
+    const int ndim = ND > 0 ? ND : m.ndim;
     double cv[GF_MAX_DIM], pv[GF_MAX_DIM];
     GF_STAGE(0);
 #pragma unroll
-    for (int d = 0; d < GF_MAX_DIM; ++d) {
+    for (int d = 0; d < (ND > 0 ? ND : GF_MAX_DIM); ++d) {
         if (d < ndim) {
             cv[d] = partner(d);
             pv[d] = own(d);
@@ -99,7 +101,7 @@ GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw&
     if (!FINISHED) gf_ens_finish_draw(A, dr);
     GF_STAGE(1);
 #pragma unroll
-    for (int d = 0; d < GF_MAX_DIM; ++d)
+    for (int d = 0; d < (ND > 0 ? ND : GF_MAX_DIM); ++d)
         if (d < ndim) q[d] = gf_ens_stretch(cv[d], pv[d], dr.z);
     GF_STAGE(2);
     double fr[3];
@@ -125,7 +127,7 @@ GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_
     const bool accept = gf_ens_move<SPEC, ILP, false>(
         m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew);
     if (accept) {
-        _Pragma("unroll") for (int d = 0; d < GF_MAX_DIM; ++d)
+        _Pragma("unroll") for (int d = 0; d < (GF_SPEC_STATIC_NDIM(SPEC) > 0 ? GF_SPEC_STATIC_NDIM(SPEC) : GF_MAX_DIM); ++d)
                         if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
         A.lnp[c * A.nwalkers + k] = lnew;
     }

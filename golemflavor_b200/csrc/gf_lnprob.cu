@@ -37,11 +37,35 @@ enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 /* LAYOUT (compile-time layouts only): 0 = strided theta (runtime ld_point / ld_dim); 1 = contiguous rows
  * (ld_dim == 1): every read is one load at a constant offset from the row pointer; 2 = packed rows of an even
  * number of doubles on a 16-byte boundary: the row arrives in ndim/2 128-bit loads. */
+/* Points per thread of the BSM kernels: a thread evaluates point i and then point i + blockDim.x, and asks for the
+ * second point's row (prefetch.global.L1) before it starts on the first.  Every thread otherwise begins with a
+ * ~1 us wait for its theta row (the first use of theta -- the prior's box test -- held 12 % of the kernel's stall
+ * samples, profiles/r02a_lnprob.md): with two points per thread that wait is paid once per two points, while the work
+ * granularity stays fine (128 points per block). */
+#ifndef GF_LP_PTS
+#define GF_LP_PTS 2
+#endif
+#define GF_LP_PTS_FOR(SPEC, KIND) ((GF_SPEC_IS_FIXED(SPEC) && (KIND) != GF_K_LNPRIOR) ? GF_LP_PTS : 1) /* the generic specialisation sits at the register limit already */
+
 template <int KIND, int SPEC, int LAYOUT = 0>
 __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int PTS = GF_LP_PTS_FOR(SPEC, KIND);
+    int64_t i = (int64_t)blockIdx.x * (blockDim.x * PTS) + threadIdx.x;
+    if (i >= n) return;
+    if constexpr (PTS > 1) {
+        if (LAYOUT != 0 || th.ld_dim == 1) { /* contiguous rows: one or two 32-byte sectors ahead of time */
+            const int64_t nxt = i + blockDim.x;
+            if (nxt < n) {
+                const char* r = reinterpret_cast<const char*>(th.p + nxt * th.ld_point);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r + (m.ndim - 1) * 8));
+            }
+        }
+    }
+#pragma unroll 1
+    for (int pt = 0; pt < PTS; ++pt, i += blockDim.x) {
     if (i >= n) return;
     const double* __restrict__ row = th.p + i * th.ld_point;
     /* the point: prior + physics + likelihood on whatever `get` reads theta from */
@@ -97,13 +121,14 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_L
          * with a compile-time layout every k is a constant and repeated reads of a column are one load) */
         evaluate([&](int k) { return __ldg(row + (int64_t)k * th.ld_dim); }, std::integral_constant<int, 2>{});
     }
+    } /* points of this thread */
 }
 
 /* one launch of k_lnprob: specialisation from the model, theta layout from the view */
 template <int KIND>
 static void launch_lnprob(const gf_dev_model& d, int spec, const gf_theta_view& th, int64_t n, double* d_lnp, double* d_fr, uint8_t* d_status,
                           cudaStream_t stream) {
-    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS);
+    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS * GF_LP_PTS_FOR(spec, KIND));
     const bool rows = th.ld_dim == 1;
     const bool packed16 = rows && th.ld_point == d.ndim && (reinterpret_cast<uintptr_t>(th.p) & 15u) == 0;
 #define GF_LP_LAUNCH(SPEC, LAYOUT, SMEM) k_lnprob<KIND, SPEC, LAYOUT><<<blocks, GF_LP_THREADS, SMEM, stream>>>(d, th, n, d_lnp, d_fr, d_status)

@@ -230,9 +230,10 @@ class DeviceEnsembleSampler(object):
         tau = np.array([integrated_time(np.swapaxes(x, 0, 1), c=c) for x in ch])
         return self._squeeze(tau)
 
-    def run_mcmc(self, pos0, N, lnprob0=None, thin=1, store=True, return_tensor=False):
+    def run_mcmc(self, pos0, N, lnprob0=None, thin=1, store=True, return_tensor=False, check_nan=True):
         """Advance all chains by N steps.  pos0 [nwalkers, ndim] or [nchains, nwalkers, ndim]
-        (None: continue).  Returns (pos, lnprob, None) like emcee."""
+        (None: continue).  Returns (pos, lnprob, None) like emcee.  ``check_nan=False`` skips emcee's NaN check of
+        the initial log-posteriors (it needs a device synchronisation) for callers that seed inside the prior box."""
         import ctypes as C
         _lib = self._lib
         torch = _lib.torch_cuda()
@@ -247,7 +248,7 @@ class DeviceEnsembleSampler(object):
             lnp = self.lnprob.evaluate(pos.reshape(-1, self.dim)).reshape(self.nchains, self.k)
         # emcee raises on a NaN log-probability; only freshly supplied positions can carry one (the move
         # rejects NaN proposals), and skipping the check on continuation keeps run_mcmc asynchronous
-        if pos0 is not None and bool(torch.isnan(lnp).any()):
+        if check_nan and pos0 is not None and bool(torch.isnan(lnp).any()):
             raise ValueError('lnprob returned NaN.')
         nstore = int(N) // int(thin) if store else 0
         chain = torch.empty((self.nchains, self.k, nstore, self.dim), dtype=torch.float64, device='cuda') if nstore else None

@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib, llh
 from . import model as _model
 from .enums import ParamTag, Texture
-from .mcmc import DeviceEnsembleSampler, flat_seed
+from .mcmc import DeviceEnsembleSampler
 from .param import Param, ParamSet
 from .scan import DEFAULT_BINNING, _dist, shard_range, sm_paramset
 
@@ -39,6 +39,21 @@ def sweep_paramset(dimension):
 
 
 _STREAMS = {}
+_MODELS = {}
+
+
+def _sweep_model(dim, texture, src, inj, smearing, binning):
+    """(LnProb, ParamSet, seed boxes) of one operator dimension, cached across sweeps."""
+    key = (int(dim), str(texture), tuple(np.asarray(src, dtype=np.float64)), tuple(np.asarray(inj, dtype=np.float64)), float(smearing),
+           np.asarray(binning, dtype=np.float64).tobytes())
+    hit = _MODELS.get(key)
+    if hit is None:
+        pset = sweep_paramset(dim)
+        args = Namespace(source_ratio=src / src.sum(), dimension=int(dim), texture=texture, binning=np.asarray(binning),
+                         no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing))
+        hit = _MODELS[key] = (llh.LnProb(args, None, pset), pset, np.array(pset.seeds, dtype=np.float64))
+    return hit
+
 
 
 def _dim_stream(torch, dim):
@@ -76,22 +91,21 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
     for dim in sorted({d for d, _ in mine}):
         idx = [start + i for i, (d, _) in enumerate(mine) if d == dim]
         scales = np.array([grid[i][1] for i in idx])
-        pset = sweep_paramset(dim)
-        args = Namespace(source_ratio=src / src.sum(), dimension=dim, texture=texture, binning=np.asarray(binning),
-                         no_bsm=False, injected_ratio=inj / inj.sum(), smearing=float(smearing))
-        fn = llh.LnProb(args, None, pset)
+        # the host side of a dimension costs as much as its share of the kernel time if done naively (the launches of the
+        # LAST dimension wait for the preparation of all the others): flattened models are cached, seeds drawn in one call
+        fn, pset, seeds = _sweep_model(dim, texture, src, inj, smearing, binning)
         nchains, ndim = len(idx), len(pset)
-        state = np.random.get_state()
-        np.random.seed(rng.randint(2 ** 31 - 1))
-        p0 = np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)])
-        np.random.set_state(state)
+        # == np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)]) with np.random seeded per dimension: one C-ordered
+        # draw consumes the stream exactly like the consecutive per-chain calls of mcmc.flat_seed (mcmc.py:88-96)
+        sub = np.random.RandomState(rng.randint(2 ** 31 - 1))
+        p0 = sub.uniform(low=seeds[:, 0], high=seeds[:, 1], size=(nchains, nwalkers, ndim))
         p0[:, :, ndim - 1] = scales[:, None]                      # frozen column: identical in all walkers
         stream = _dim_stream(torch, dim)
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
             sampler = DeviceEnsembleSampler(nwalkers, ndim, fn, nchains=nchains, seed=seed + 1000 * dim, nfree=ndim - 1,
                                             chain0=idx[0])
-            sampler.run_mcmc(p0, burnin, store=False, return_tensor=True)
+            sampler.run_mcmc(p0, burnin, store=False, return_tensor=True, check_nan=False)   # seeds lie inside the prior box
             sampler.reset()
             pos, lnp, _ = sampler.run_mcmc(None, nsteps, store=False, return_tensor=True)
             # summaries from the final ensemble + the acceptance counters (no chain leaves the device)

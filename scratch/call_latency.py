@@ -23,3 +23,15 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(2000): f2(th)
 pr.disable()
 pstats.Stats(pr).sort_stats('cumulative').print_stats(18)
+# device tensors in, device tensors out: torch.ops.golemflavor.lnprob against the ctypes binding of the same entry point
+from golemflavor_b200 import _lib
+lib = _lib.load()
+tht = torch.as_tensor(th).cuda()
+out = torch.empty(512, dtype=torch.float64, device='cuda')
+for label, call in (('torch.ops', lambda: f2.evaluate(tht)),
+                    ('ctypes   ', lambda: _lib.check(lib.gf_lnprob(f2.model.ref, _lib.ptr(tht), 512, 6, 1, _lib.ptr(out), None, None, _lib.stream_ptr(torch))))):
+    for _ in range(50): call()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(5000): call()
+    torch.cuda.synchronize()
+    print('device tensor call through %s: %.1f us' % (label, (time.perf_counter() - t0) / 5000 * 1e6))

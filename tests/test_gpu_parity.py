@@ -1210,3 +1210,61 @@ def test_reference_call_variants(torch, golden):
     assert np.array_equal(h_fr[~np.isnan(h_fr)], frs[~np.isnan(frs)])
     with pytest.raises(ValueError):
         fn.evaluate_host(th, fr=np.empty((5, 3)))
+
+
+def test_torch_ops_equal_the_c_abi(torch, golden):
+    """`torch.ops.golemflavor.*` (csrc/gf_torch_ops.cpp) against the ctypes binding of the same entry points: identical
+    bits, current-stream semantics, reference-style exceptions."""
+    g = golden('ref_llh.npz')
+    ops, lib = _lib.torch_ops(), _lib.load()
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
+    fn = llh.LnProb(args, asimov, pset)
+    th = torch.as_tensor(models.draw_in_ranges(pset, 5000, np.random.default_rng(2))).cuda()
+    lnp, frs, st = ops.lnprob(th, fn.model.blob, True, True)
+    ref_l, ref_f = torch.empty(5000, dtype=torch.float64, device='cuda'), torch.empty((5000, 3), dtype=torch.float64, device='cuda')
+    ref_s = torch.empty(5000, dtype=torch.uint8, device='cuda')
+    _lib.check(lib.gf_lnprob(fn.model.ref, _lib.ptr(th), 5000, fn.ndim, 1, _lib.ptr(ref_l), _lib.ptr(ref_f), _lib.ptr(ref_s), _lib.stream_ptr(torch)))
+    assert torch.equal(lnp, ref_l) and torch.equal(frs.nan_to_num(), ref_f.nan_to_num()) and torch.equal(st, ref_s)
+    only, e1, e2 = ops.lnprob(th, fn.model.blob, False, False)
+    assert torch.equal(only, ref_l) and e1.numel() == 0 and e2.numel() == 0
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                     # the operator runs on torch's CURRENT stream
+        again = ops.lnprob(th, fn.model.blob, False, False)[0]
+    side.synchronize()
+    assert torch.equal(again, ref_l)
+    f2, s2 = ops.flux_averaged_fr(th, fn.model.blob)
+    inside = ~(st & _lib.ST_OUT_OF_PRIOR).bool()        # gf_lnprob leaves NaN compositions for out-of-prior points
+    assert torch.equal(f2[inside], frs[inside]) and torch.equal(s2[inside], st[inside])
+    assert np.allclose(ops.lnprior(th, fn.model.blob).cpu().numpy(), llh.lnprior(th, pset).cpu().numpy(), rtol=0, atol=0, equal_nan=True)
+    ang = th[:, :4].contiguous()
+    u = ops.angles_to_u(ang)
+    assert u.dtype == torch.complex128 and np.array_equal(u.cpu().numpy(), fr.angles_to_u(ang).cpu().numpy())
+    src = torch.tensor([1.0, 2.0, 0.0], dtype=torch.float64, device='cuda')
+    assert np.array_equal(ops.u_to_fr(src, u).cpu().numpy(), fr.u_to_fr(src, u).cpu().numpy())
+    hist, kept = torch.zeros(26 ** 3, dtype=torch.int64, device='cuda'), torch.zeros(1, dtype=torch.int64, device='cuda')
+    fm = scan.scan_model('unitary')
+    ops.scan_hist(fm.blob, 26, 0, 100000, 25, hist, kept)
+    h2, k2 = scan.scan_histogram(fm, 100000, nb=25, seed=26, distributed=False)
+    assert int(kept) == k2 == 100000 and np.array_equal(hist.cpu().numpy().reshape(26, 26, 26), h2)
+    bad = model.FlatModel(model.physics_model(no_bsm=False, dimension=6, binning=models.BINNING, loglam=-40.0))
+    bad.struct.dimension = 99                         # the blob shares memory with the struct
+    with pytest.raises(ValueError):                   # GF_ERR_ARG -> ValueError, like the ctypes path and fr.py:198-202
+        ops.lnprob(torch.zeros((4, 1), dtype=torch.float64, device='cuda'), bad.blob, False, False)
+    with pytest.raises(RuntimeError):                 # wrong column count
+        ops.lnprob(th[:, :5].contiguous(), fn.model.blob, False, False)
+
+
+def test_multi_gpu_nccl_scan_evidence_and_sweep_are_rank_count_invariant(torch):
+    """tests/dist_scan_check.py under torchrun on every GPU of the box (NCCL): sharded scan histograms bit-identical to
+    the single-rank ones, evidence-grid merge and the sweep invariant.  Needs >= 2 GPUs (skipped on the 1-GPU test box;
+    the 2- and 8-rank outputs of this round are committed under profiles/)."""
+    import subprocess
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs at least two GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n), '--master-addr', '127.0.0.1',
+                          '--master-port', '29731', os.path.join(root, 'tests', 'dist_scan_check.py')], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]
+    assert res.stdout.count('bit-identical=True') == 3 and 'ok=True' in res.stdout and 'sweep=True' in res.stdout

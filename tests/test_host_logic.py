@@ -37,6 +37,24 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert lib.gf_sizeof(0) == C.sizeof(_lib.Model)
 
 
+def test_torch_ops_library_builds_and_registers_every_operator():
+    """The `torch.ops.golemflavor.*` registration of the C ABI (csrc/gf_torch_ops.cpp) builds in-tree, loads and
+    defines every operator `_lib.TORCH_OPS` names (no compute call without a GPU)."""
+    import torch
+    path = build.build_torch_ops()
+    assert os.path.exists(path) and path == _lib.TORCH_OPS_PATH
+    ops = _lib.torch_ops()
+    assert int(ops.abi_version()) == 1
+    for name in _lib.TORCH_OPS:
+        assert hasattr(ops, name), name
+    schema = str(torch.ops.golemflavor.lnprob.default._schema)
+    assert 'Tensor theta' in schema and 'bool want_fr' in schema
+    # argument validation happens before any CUDA call: a CPU theta is refused
+    fm = model.physics_model(ndim=1)
+    with pytest.raises(RuntimeError):
+        ops.lnprob(torch.zeros((2, 1), dtype=torch.float64), model.FlatModel(fm).blob, False, False)
+
+
 def test_no_oracle_or_cpu_fallback_in_product():
     """The product package must not import the oracle or the host harness."""
     pkg = os.path.join(ROOT, 'golemflavor_b200')
