@@ -391,6 +391,22 @@ def run_gpu(opts):
         torch.cuda.synchronize()
         link = max(link, theta_host.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
     link_min = min_over_ranks(link)
+    # ... and the same input copy while the step's results stream back on a second stream, as they do inside the pipeline
+    # (H2D 56 B + D2H 8 B per point): the ceiling the pipeline itself can reach on this host
+    link_bidir, side = 0.0, torch.cuda.Stream()
+    for _ in range(3):
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            out_host.copy_(out, non_blocking=True)
+        theta.copy_(theta_host, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(side)
+        c1.record()
+        torch.cuda.synchronize()
+        link_bidir = max(link_bidir, theta_host.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    link_bidir_min = min_over_ranks(link_bidir)
     finite_frac = float(np.isfinite(out_np).mean())
 
     # -- secondary: sharded Monte-Carlo scan with the histogram all-reduce (config 4)
@@ -550,6 +566,8 @@ def run_gpu(opts):
             'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': n * fn.ndim * 8, 'd2h_bytes_per_step': n * 8,
                     'steps': e2e_steps, 'api': 'llh.LnProb.evaluate_host -> gf_lnprob_host (pinned host buffers)',
                     'h2d_gbs': e2e_value / world * fn.ndim * 8 / 1e9, 'h2d_link_gbs': link, 'h2d_link_gbs_min_over_ranks': link_min,
+                    'h2d_link_gbs_with_d2h': link_bidir, 'h2d_link_gbs_with_d2h_min_over_ranks': link_bidir_min,
+                    'link_note': 'plain pinned copies of the same buffers, all ranks at the same time after a barrier',
                     'numa_node': numa},
             'gpu_launches': int(launches),
             'clocks': clock_info,

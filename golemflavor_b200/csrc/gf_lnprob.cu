@@ -18,6 +18,7 @@
  */
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 
@@ -194,27 +195,38 @@ extern "C" int gf_lnprior(const gf_model* model, const double* d_theta, int64_t 
 
 namespace {
 
-constexpr int kSlots = 3;               /* H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c */
+/* Ring of (H2D, kernel, D2H) slots: H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c.  Defaults: 3
+ * slots of 2^18 points; GF_HOST_SLOTS (2..8) and GF_HOST_CHUNK_LOG2 (12..24) in the environment override them when a
+ * process first uses the pipeline (deeper rings ride out host-thread wake-up jitter when many ranks share one host). */
+constexpr int kMaxSlots = 8;
 #ifndef GF_HOST_CHUNK_LOG2
 #define GF_HOST_CHUNK_LOG2 18
 #endif
-constexpr int64_t kChunkPoints = 1ll << GF_HOST_CHUNK_LOG2;
 constexpr int kMaxPipeDevices = 64;
+
+int env_int(const char* name, int fallback, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v || !*v) return fallback;
+    const long x = strtol(v, nullptr, 10);
+    return x < lo ? lo : x > hi ? hi : (int)x;
+}
 
 /* One pipeline per device ordinal (a process may drive several GPUs); created on first use, kept for the
  * life of the process. */
 struct HostPipe {
-    cudaStream_t stream[kSlots] = {};
-    cudaEvent_t done[kSlots] = {};
-    double* d_theta[kSlots] = {};
-    double* d_lnp[kSlots] = {};
-    double* d_fr[kSlots] = {};
-    uint8_t* d_st[kSlots] = {};
+    int slots = 3;
+    int64_t chunk = 1ll << GF_HOST_CHUNK_LOG2;
+    cudaStream_t stream[kMaxSlots] = {};
+    cudaEvent_t done[kMaxSlots] = {};
+    double* d_theta[kMaxSlots] = {};
+    double* d_lnp[kMaxSlots] = {};
+    double* d_fr[kMaxSlots] = {};
+    uint8_t* d_st[kMaxSlots] = {};
     /* pinned staging for pageable caller buffers */
-    double* s_theta[kSlots] = {};
-    double* s_lnp[kSlots] = {};
-    double* s_fr[kSlots] = {};
-    uint8_t* s_st[kSlots] = {};
+    double* s_theta[kMaxSlots] = {};
+    double* s_lnp[kMaxSlots] = {};
+    double* s_fr[kMaxSlots] = {};
+    uint8_t* s_st[kMaxSlots] = {};
     bool ready = false, staged = false;
 };
 
@@ -222,7 +234,7 @@ std::mutex g_pipe_mutex;
 HostPipe g_pipes[kMaxPipeDevices];
 
 void pipe_release(HostPipe& p) {
-    for (int s = 0; s < kSlots; ++s) {
+    for (int s = 0; s < kMaxSlots; ++s) {
         if (p.stream[s]) cudaStreamDestroy(p.stream[s]);
         if (p.done[s]) cudaEventDestroy(p.done[s]);
         cudaFree(p.d_theta[s]);
@@ -233,22 +245,30 @@ void pipe_release(HostPipe& p) {
     cudaGetLastError();
     const HostPipe fresh;
     /* staging buffers (if any) survive: they are host memory, independent of what failed */
-    double* st[kSlots]; double* sl[kSlots]; double* sf[kSlots]; uint8_t* ss[kSlots];
-    for (int s = 0; s < kSlots; ++s) { st[s] = p.s_theta[s]; sl[s] = p.s_lnp[s]; sf[s] = p.s_fr[s]; ss[s] = p.s_st[s]; }
+    double* st[kMaxSlots]; double* sl[kMaxSlots]; double* sf[kMaxSlots]; uint8_t* ss[kMaxSlots];
+    for (int s = 0; s < kMaxSlots; ++s) { st[s] = p.s_theta[s]; sl[s] = p.s_lnp[s]; sf[s] = p.s_fr[s]; ss[s] = p.s_st[s]; }
     const bool staged = p.staged;
+    const int slots = p.slots;
+    const int64_t chunk = p.chunk;
     p = fresh;
-    for (int s = 0; s < kSlots; ++s) { p.s_theta[s] = st[s]; p.s_lnp[s] = sl[s]; p.s_fr[s] = sf[s]; p.s_st[s] = ss[s]; }
+    for (int s = 0; s < kMaxSlots; ++s) { p.s_theta[s] = st[s]; p.s_lnp[s] = sl[s]; p.s_fr[s] = sf[s]; p.s_st[s] = ss[s]; }
     p.staged = staged;
+    p.slots = slots;
+    p.chunk = chunk;
 }
 
 int pipe_init_unchecked(HostPipe& p) {
-    for (int s = 0; s < kSlots; ++s) {
+    if (!p.staged) { /* the geometry is fixed once any buffer of this pipeline exists */
+        p.slots = env_int("GF_HOST_SLOTS", 3, 2, kMaxSlots);
+        p.chunk = 1ll << env_int("GF_HOST_CHUNK_LOG2", GF_HOST_CHUNK_LOG2, 12, 24);
+    }
+    for (int s = 0; s < p.slots; ++s) {
         GF_CUDA(cudaStreamCreateWithFlags(&p.stream[s], cudaStreamNonBlocking));
         GF_CUDA(cudaEventCreateWithFlags(&p.done[s], cudaEventDisableTiming));
-        GF_CUDA(cudaMalloc(&p.d_theta[s], kChunkPoints * GF_MAX_DIM * sizeof(double)));
-        GF_CUDA(cudaMalloc(&p.d_lnp[s], kChunkPoints * sizeof(double)));
-        GF_CUDA(cudaMalloc(&p.d_fr[s], kChunkPoints * 3 * sizeof(double)));
-        GF_CUDA(cudaMalloc(&p.d_st[s], kChunkPoints));
+        GF_CUDA(cudaMalloc(&p.d_theta[s], p.chunk * GF_MAX_DIM * sizeof(double)));
+        GF_CUDA(cudaMalloc(&p.d_lnp[s], p.chunk * sizeof(double)));
+        GF_CUDA(cudaMalloc(&p.d_fr[s], p.chunk * 3 * sizeof(double)));
+        GF_CUDA(cudaMalloc(&p.d_st[s], p.chunk));
     }
     return GF_OK;
 }
@@ -276,11 +296,11 @@ bool is_pinned(const void* ptr) {
 
 int staging_init(HostPipe& p) {
     if (p.staged) return GF_OK;
-    for (int s = 0; s < kSlots; ++s) {
-        if (!p.s_theta[s]) GF_CUDA(cudaHostAlloc(&p.s_theta[s], kChunkPoints * GF_MAX_DIM * sizeof(double), cudaHostAllocDefault));
-        if (!p.s_lnp[s]) GF_CUDA(cudaHostAlloc(&p.s_lnp[s], kChunkPoints * sizeof(double), cudaHostAllocDefault));
-        if (!p.s_fr[s]) GF_CUDA(cudaHostAlloc(&p.s_fr[s], kChunkPoints * 3 * sizeof(double), cudaHostAllocDefault));
-        if (!p.s_st[s]) GF_CUDA(cudaHostAlloc(&p.s_st[s], kChunkPoints, cudaHostAllocDefault));
+    for (int s = 0; s < p.slots; ++s) {
+        if (!p.s_theta[s]) GF_CUDA(cudaHostAlloc(&p.s_theta[s], p.chunk * GF_MAX_DIM * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_lnp[s]) GF_CUDA(cudaHostAlloc(&p.s_lnp[s], p.chunk * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_fr[s]) GF_CUDA(cudaHostAlloc(&p.s_fr[s], p.chunk * 3 * sizeof(double), cudaHostAllocDefault));
+        if (!p.s_st[s]) GF_CUDA(cudaHostAlloc(&p.s_st[s], p.chunk, cudaHostAllocDefault));
     }
     p.staged = true;
     return GF_OK;
@@ -291,6 +311,8 @@ int pipe_run(HostPipe& p, const gf_dev_model& d, bool direct, const double* h_th
              uint8_t* h_status) {
     const int ndim = d.ndim;
     const int spec = gf_model_spec(d);
+    const int kSlots = p.slots;
+    const int64_t kChunkPoints = p.chunk;
     const int64_t nchunks = (n + kChunkPoints - 1) / kChunkPoints;
     /* results of chunk c staged in slot c % kSlots are copied out before the slot is reused */
     auto drain = [&](int64_t c) -> int {
@@ -352,7 +374,7 @@ extern "C" int gf_lnprob_host(const gf_model* model, const double* h_theta, int6
     if (rc != GF_OK) {
         /* the caller is about to be told that the call failed: no copy may still be writing into its buffers
          * (or reading the staging ring) after we return */
-        for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(p.stream[s]);
+        for (int s = 0; s < p.slots; ++s) cudaStreamSynchronize(p.stream[s]);
         cudaGetLastError();
     }
     return rc;

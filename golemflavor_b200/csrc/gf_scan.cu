@@ -531,7 +531,9 @@ int evg_plan(K kern, int nscales, uint64_t count, evg_geometry* geo) {
     GF_REQUIRE(per_sm >= 1, "gf_scan_evidence_grid: kernel does not fit on an SM (smem %zu B)", smem);
     const int ny = (nscales + s_per - 1) / s_per;
     const uint64_t want = (count + GF_SCAN_THREADS - 1) / GF_SCAN_THREADS;
-    uint64_t nx = ((uint64_t)sms * per_sm + ny - 1) / ny;
+    /* every block carries the same amount of work: the grid must fit the device in ONE wave (rounding the x extent up
+     * would leave a few blocks for a second wave that takes as long as the first) */
+    uint64_t nx = ((uint64_t)sms * per_sm) / ny;
     if (nx > want) nx = want;
     if (nx < 1) nx = 1;
     geo->s_per = s_per; geo->ny = ny; geo->per_sm = per_sm; geo->nx = (unsigned)nx; geo->smem = smem;

@@ -84,7 +84,6 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
     rows = torch.zeros((len(grid), 8), dtype=torch.float64, device='cuda')
     src = np.asarray(source_ratio, dtype=np.float64)
     inj = np.asarray(injected_ratio, dtype=np.float64)
-    rng = np.random.RandomState(seed)
     # one CUDA stream per dimension: the launches of different dimensions (different models, hence different
     # kernel launches) are latency-bound single-warp clusters and run side by side on the SMs
     pending = []
@@ -95,10 +94,13 @@ def sweep(dimensions=(3, 4, 5, 6, 7, 8), segments=100, texture=Texture.OET, sour
         # LAST dimension wait for the preparation of all the others): flattened models are cached, seeds drawn in one call
         fn, pset, seeds = _sweep_model(dim, texture, src, inj, smearing, binning)
         nchains, ndim = len(idx), len(pset)
-        # == np.stack([flat_seed(pset, nwalkers) for _ in range(nchains)]) with np.random seeded per dimension: one C-ordered
-        # draw consumes the stream exactly like the consecutive per-chain calls of mcmc.flat_seed (mcmc.py:88-96)
-        sub = np.random.RandomState(rng.randint(2 ** 31 - 1))
-        p0 = sub.uniform(low=seeds[:, 0], high=seeds[:, 1], size=(nchains, nwalkers, ndim))
+        # == np.stack([flat_seed(pset, nwalkers) for every chain of the dimension]) with np.random seeded per dimension:
+        # one C-ordered draw consumes the stream exactly like consecutive per-chain calls of mcmc.flat_seed
+        # (mcmc.py:88-96).  The stream is a function of (seed, dimension) and is drawn for ALL chains of the dimension,
+        # of which this rank keeps its own: the sweep is identical however the grid is sharded over ranks.
+        sub = np.random.RandomState((int(seed) * 1000003 + dim) % (2 ** 31 - 1))
+        first = [i for i, (d, _) in enumerate(grid) if d == dim][0]
+        p0 = sub.uniform(low=seeds[:, 0], high=seeds[:, 1], size=(int(segments), nwalkers, ndim))[[i - first for i in idx]]
         p0[:, :, ndim - 1] = scales[:, None]                      # frozen column: identical in all walkers
         stream = _dim_stream(torch, dim)
         stream.wait_stream(torch.cuda.current_stream())
