@@ -39,8 +39,10 @@ extern std::atomic<unsigned long long> g_gf_launches;
 template <bool COOP, int SPEC, int ILP>
 __global__ void __launch_bounds__(GF_ENS_THREADS)
     k_ensemble(const __grid_constant__ gf_dev_model m, const gf_ens_args A, const int64_t one_step, const int one_half) {
+    constexpr int LANES = GF_ENS_LANES(SPEC);
     const int half = A.nwalkers / 2;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LANES; /* walker pair of this thread */
+    const int lane = (int)(threadIdx.x % LANES);
     const int64_t total = A.nchains * half;
     const bool active = tid < total;
     const int64_t c = active ? tid / half : 0;
@@ -53,14 +55,14 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 if (active) {
-                    const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, h * half + w, h, A.step0 + s);
+                    const unsigned acc = gf_ens_update<SPEC, ILP, LANES>(m, A, c, h * half + w, h, A.step0 + s, lane);
                     acc0 += h ? 0u : acc;
                     acc1 += h ? acc : 0u;
                 }
                 __threadfence();
                 grid.sync();
             }
-            if (active && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) {
+            if (active && lane == 0 && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) {
                 gf_ens_store(m, A, c, w, (s + 1) / A.thin - 1, nstore);
                 gf_ens_store(m, A, c, half + w, (s + 1) / A.thin - 1, nstore);
             }
@@ -68,11 +70,11 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
     } else if (active) {
         const int64_t s = one_step;
         if (one_half < 2) {
-            const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, one_half * half + w, one_half, A.step0 + s);
+            const unsigned acc = gf_ens_update<SPEC, ILP, LANES>(m, A, c, one_half * half + w, one_half, A.step0 + s, lane);
             acc0 = one_half ? 0u : acc;
             acc1 = one_half ? acc : 0u;
         }
-        if (one_half == 2 && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) { /* store pass */
+        if (one_half == 2 && lane == 0 && (s + 1) % A.thin == 0 && (s + 1) / A.thin <= nstore) { /* store pass */
             gf_ens_store(m, A, c, w, (s + 1) / A.thin - 1, nstore);
             gf_ens_store(m, A, c, half + w, (s + 1) / A.thin - 1, nstore);
         }
@@ -94,14 +96,16 @@ __global__ void __launch_bounds__(GF_ENS_THREADS)
 template <int SPEC, int ILP>
 __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
     k_ensemble_block(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
+    constexpr int LANES = GF_ENS_LANES(SPEC);
     const int half = A.nwalkers / 2;
+    const int lane = (int)(threadIdx.x % LANES);
     const int64_t c = blockIdx.x;
     const int64_t nstore = A.nsteps / A.thin;
     for (int64_t s = 0; s < A.nsteps; ++s) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-            for (int w = threadIdx.x; w < half; w += blockDim.x) {
-                const unsigned acc = gf_ens_update<SPEC, ILP>(m, A, c, h * half + w, h, A.step0 + s);
+            for (int w = threadIdx.x / LANES; w < half; w += blockDim.x / LANES) {
+                const unsigned acc = gf_ens_update<SPEC, ILP, LANES>(m, A, c, h * half + w, h, A.step0 + s, lane);
                 if (acc && A.naccept) A.naccept[c * A.nwalkers + h * half + w] += 1ull; /* owned by this thread */
             }
             __threadfence_block();
@@ -114,32 +118,41 @@ __global__ void __launch_bounds__(GF_ENS_BLOCK_MAX)
 
 
 /*
- * Cluster-per-chain variant.  CTA `rank` of the cluster owns walkers [rank*T, (rank+1)*T) of BOTH halves
- * (thread = walker pair, as above); positions and log-posteriors stay in its shared memory
- * (sh = pos[2][T][ndim], lnp[2][T]) from the first step to the last.  During half-step h every thread
- * reads its partner from the OTHER half through distributed shared memory -- that half is not written
- * during the half-step -- and updates its own walker of half h in place; the cluster barrier
- * (barrier.cluster arrive.release / wait.acquire) orders the two.  No global-memory round trip and no
- * grid barrier on the critical path: a half-step costs one log-posterior latency plus the barrier.
+ * Cluster-per-chain variant.  CTA `rank` of the cluster owns walker pairs [rank*T, (rank+1)*T): walker w of BOTH
+ * halves; positions and log-posteriors stay in its shared memory (sh = pos[2][T][ndim], lnp[2][T]) from the first
+ * step to the last.  During half-step h every thread reads its partner from the OTHER half through distributed
+ * shared memory -- that half is not written during the half-step -- and updates its own walker of half h in place;
+ * the cluster barrier (barrier.cluster arrive.release / wait.acquire) orders the two.  No global-memory round trip
+ * and no grid barrier on the critical path: a half-step costs one log-posterior latency plus the barrier.
+ * On the BSM path two adjacent lanes share one walker pair (LANES = 2, see gf_bin_loop): both run the same update and
+ * split the energy bins of its log-posterior; lane 0 writes.
+ *
+ * Measured and dropped (round 2): a dedicated producer warp per CTA that computes the next half-step's draws into a
+ * double-buffered shared-memory table while the consumers evaluate.  It took 4-6 % off a single chain (C2 2.99 ->
+ * 2.82, C3 13.2 -> 12.6 us per step) but the extra warp and the 224-register budget it forces cut the resident CTAs
+ * per SM from 5 to 3, so the 600 single-warp chains of the sensitivity sweep no longer ran in one wave (+15 %).
  */
-/* threads per CTA: 256 for the register-light SM-only models, 128 for the BSM path (full register file
- * for the eigen stage: no spills on the latency-critical path) */
-#define GF_ENS_CL_MAX_THREADS(SPEC) (GF_SPEC_IS_SM(SPEC) ? 256 : 128)
+/* consumer threads per CTA: 256 walker pairs for the register-light SM-only models, 128 walker pairs x 2 lanes on the
+ * BSM path (<= 255 registers per thread: no spills on the latency-critical path) */
+#define GF_ENS_CL_MAX_CONSUMERS 256
 template <int SPEC, int ILP>
-__global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
+__global__ void __launch_bounds__(GF_ENS_CL_MAX_CONSUMERS, 1)
     k_ensemble_cluster(const __grid_constant__ gf_dev_model m, const gf_ens_args A) {
     extern __shared__ double sh_ens[];
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC); /* compile-time layouts: constant dimension count */
-    const int T = (int)blockDim.x, ndim = ND > 0 ? ND : m.ndim, half = A.nwalkers / 2;
+    constexpr int LANES = GF_ENS_LANES(SPEC);
+    /* T = walker pairs of this CTA: with two lanes per walker (BSM) threads 2 wl and 2 wl + 1 share walker pair wl */
+    const int T = (int)blockDim.x / LANES, ndim = ND > 0 ? ND : m.ndim, half = A.nwalkers / 2;
     const int nc = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int64_t c = blockIdx.x / nc;
-    const int wl = (int)threadIdx.x, w = rank * T + wl;
+    const int wl = (int)threadIdx.x / LANES, lane = (int)threadIdx.x % LANES, w = rank * T + wl;
     const bool active = w < half;
+    const bool writer = active && lane == 0;
     double* pos_s = sh_ens;
     double* lnp_s = sh_ens + 2 * T * ndim;
     const int64_t nstore = A.nsteps / A.thin;
-    if (active) {
+    if (writer) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int64_t k = c * A.nwalkers + h * half + w;
@@ -182,7 +195,10 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 double* p = pos_s + (h * T + wl) * ndim;
                 double q[GF_MAX_DIM];
                 double lnew;
-                if (gf_ens_move<SPEC, ILP, true>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; }, lnp_s[h * T + wl], q, lnew)) {
+                const bool accept = gf_ens_move<SPEC, ILP, true, LANES>(m, A, dr, [&](int d) { return cj[d]; }, [&](int d) { return p[d]; },
+                                                                         lnp_s[h * T + wl], q, lnew, lane);
+                if (LANES > 1) __syncwarp(3u << (((unsigned)threadIdx.x & 31u) & ~1u)); /* the partner lane has read the old position */
+                if (accept && lane == 0) {
                     _Pragma("unroll") for (int d = 0; d < (ND > 0 ? ND : GF_MAX_DIM); ++d)
                         if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
                     lnp_s[h * T + wl] = lnew;
@@ -199,7 +215,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
                 GF_TICK(t_draw)
                 /* the step is complete for this thread's two walkers once its own second-half update is
                  * done (only their owner writes them): store them in the shadow of the barrier as well */
-                if (h == 1 && --until_store == 0) {
+                if (lane == 0 && h == 1 && --until_store == 0) {
                     until_store = A.thin;
                     if (stored < nstore) { /* running output pointers: no 64-bit index arithmetic per store */
                         if (A.chain) {
@@ -237,7 +253,7 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
         for (int i = 0; i < 16; ++i) gf_stage_acc[i] = 0;
     }
 #endif
-    if (active) {
+    if (writer) {
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
             const int64_t k = c * A.nwalkers + h * half + w;
@@ -257,26 +273,31 @@ __global__ void __launch_bounds__(GF_ENS_CL_MAX_THREADS(SPEC), 1)
  * i.e. per SM (measured, 1024 walkers: 6.2 us / step at 4 CTAs x 128 threads, 5.4 at 16 x 32) -- as long
  * as the clusters of all chains fit the SMs at once; never more than 16 CTAs (the non-portable maximum)
  * or max_threads per CTA.  Returns false if the ensemble does not fit a cluster. */
-static bool cluster_geometry(int64_t nchains, int half, int sms, int want_nc, int max_threads, int* nc_out, int* threads_out) {
+static bool cluster_geometry(int64_t nchains, int half, int sms, int want_nc, int max_threads, int lanes, int* nc_out, int* threads_out) {
+    /* `lanes` threads work on one walker pair: a CTA of `threads` threads holds threads / lanes pairs; warps stay whole,
+     * so the pairs per CTA come in multiples of 32 / lanes */
+    const int max_pairs = max_threads / lanes, quantum = 32 / lanes;
+    auto pairs_for = [&](int nc_) { return (((half + nc_ - 1) / nc_) + quantum - 1) / quantum * quantum; };
     int nc = 1;
     if (want_nc > 0) {
         while (nc < want_nc && nc < 16) nc *= 2;
     } else {
-        while (nc < 16 && (half + nc - 1) / nc > 32 && nchains * (nc * 2) <= (int64_t)sms) nc *= 2;
+        while (nc < 16 && (half + nc - 1) / nc > quantum && nchains * (nc * 2) <= (int64_t)sms) nc *= 2;
     }
-    while (nc < 16 && (half + nc - 1) / nc > max_threads) nc *= 2;
-    int threads = (((half + nc - 1) / nc) + 31) / 32 * 32;
-    if (threads > max_threads) return false;
-    while (nc > 1 && (nc / 2) * threads >= half) nc /= 2; /* rounding to warps may have emptied the last CTAs */
+    while (nc < 16 && (half + nc - 1) / nc > max_pairs) nc *= 2;
+    const int pairs = pairs_for(nc);
+    if (pairs > max_pairs) return false;
+    while (nc > 1 && (nc / 2) * pairs >= half) nc /= 2; /* rounding to warps may have emptied the last CTAs */
     *nc_out = nc;
-    *threads_out = threads;
+    *threads_out = pairs * lanes;
     return true;
 }
 
 template <int SPEC, int ILP>
 static int launch_cluster(const gf_dev_model& d, const gf_ens_args& A, int nc, int threads, cudaStream_t st, bool* launched) {
     auto kern = k_ensemble_cluster<SPEC, ILP>;
-    const size_t smem = (size_t)(2 * threads * d.ndim + 2 * threads) * sizeof(double);
+    const int pairs = threads / GF_ENS_LANES(SPEC);
+    const size_t smem = (size_t)(2 * pairs * d.ndim + 2 * pairs) * sizeof(double);
     GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (nc > 8) GF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     cudaLaunchConfig_t cfg = {};
@@ -305,15 +326,16 @@ static int launch_cluster(const gf_dev_model& d, const gf_ens_args& A, int nc, i
 
 template <int SPEC, int ILP>
 static int run_spec(const gf_dev_model& d, const gf_ens_args& A, const gf_ensemble_config* cfg, cudaStream_t st) {
+    constexpr int LANES = GF_ENS_LANES(SPEC);
     const int half = cfg->nwalkers / 2;
-    const int64_t total = cfg->nchains * half;
+    const int64_t total = cfg->nchains * half * LANES; /* threads of the grid-barrier shape */
     const unsigned blocks = gf_blocks_for(total, GF_ENS_THREADS);
     int sms = 0;
     if (int rc = gf_sm_count(&sms)) return rc;
-    /* auto: the cluster shape whenever the ensemble fits one (<= 16 x 256 walker pairs, 16 x 128 on the BSM path) */
+    /* auto: the cluster shape whenever the ensemble fits one (<= 16 x 256 walker pairs, 16 x 128 pairs x 2 lanes on the BSM path) */
     if (cfg->mode == 3 || cfg->mode == 0) {
         int nc = 0, threads = 0;
-        if (cluster_geometry(cfg->nchains, half, sms, cfg->cluster_blocks, GF_ENS_CL_MAX_THREADS(SPEC), &nc, &threads)) {
+        if (cluster_geometry(cfg->nchains, half, sms, cfg->cluster_blocks, GF_ENS_CL_MAX_CONSUMERS, LANES, &nc, &threads)) {
             for (;;) {
                 bool launched = false;
                 if (int rc = launch_cluster<SPEC, ILP>(d, A, nc, threads, st, &launched)) return rc;
@@ -323,16 +345,16 @@ static int run_spec(const gf_dev_model& d, const gf_ens_args& A, const gf_ensemb
                 }
                 /* this cluster size cannot be scheduled on the device: halve it while the CTA still holds its share */
                 nc /= 2;
-                threads = nc >= 1 ? (((half + nc - 1) / nc) + 31) / 32 * 32 : 0;
-                if (nc < 1 || threads > GF_ENS_CL_MAX_THREADS(SPEC)) break;
+                threads = nc >= 1 ? ((((half + nc - 1) / nc) * LANES) + 31) / 32 * 32 : 0;
+                if (nc < 1 || threads > GF_ENS_CL_MAX_CONSUMERS) break;
             }
         }
         GF_REQUIRE(cfg->mode == 0, "gf_ensemble_run: mode 3 (cluster per chain) cannot hold %d walkers per chain", cfg->nwalkers);
     }
     /* block mode only when every thread owns ONE walker pair -- a second sequential pass per half-step
      * costs more than the grid barrier it saves (measured: 1024 walkers, 24 vs 12 us / step) */
-    if (cfg->mode == 2 || (cfg->mode == 0 && half <= GF_ENS_BLOCK_MAX)) {
-        const int threads = half >= GF_ENS_BLOCK_MAX ? GF_ENS_BLOCK_MAX : ((half + 31) / 32) * 32;
+    if (cfg->mode == 2 || (cfg->mode == 0 && half * LANES <= GF_ENS_BLOCK_MAX)) {
+        const int threads = half * LANES >= GF_ENS_BLOCK_MAX ? GF_ENS_BLOCK_MAX : ((half * LANES + 31) / 32) * 32;
         k_ensemble_block<SPEC, ILP><<<(unsigned)cfg->nchains, threads, 0, st>>>(d, A);
         ++g_gf_launches;
         GF_LAUNCH_CHECK("k_ensemble_block");

@@ -83,9 +83,16 @@ GF_HD double gf_ens_stretch(double cd, double pd, double z) { return GF_SUB_RN(c
  * (false for NaN).  FINISHED: gf_ens_finish_draw has already run (the cluster kernel does it in the shadow
  * of the barrier); otherwise it runs here, in the shadow of the loads.
  */
-template <int SPEC, int ILP, bool FINISHED, class LoadPartner, class LoadOwn>
+/* LANES = 2: lanes 2w and 2w + 1 of a warp run the same update (same draws, same proposal) and share the energy bins of
+ * its log-posterior (gf_bin_loop); both obtain the same decision.  `lane` = threadIdx.x & 1. */
+#ifndef GF_ENS_BSM_LANES
+#define GF_ENS_BSM_LANES 2 /* developer builds: 1 = one thread per walker pair on the BSM path as well */
+#endif
+#define GF_ENS_LANES(SPEC) (GF_SPEC_IS_SM(SPEC) ? 1 : GF_ENS_BSM_LANES)
+
+template <int SPEC, int ILP, bool FINISHED, int LANES = 1, class LoadPartner, class LoadOwn>
 GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw& dr, LoadPartner partner, LoadOwn own, double lold,
-                       double* q, double& lnew) {
+                       double* q, double& lnew, int lane = 0) {
     /* with a compile-time layout the dimension count is a constant: no guarded work on the 16 - ndim unused slots */
     constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC);
     const int ndim = ND > 0 ? ND : m.ndim;
@@ -106,15 +113,15 @@ GF_HD bool gf_ens_move(const gf_dev_model& m, const gf_ens_args& A, gf_ens_draw&
     GF_STAGE(2);
     double fr[3];
     unsigned st = 0u;
-    lnew = gf_point_lnprob<SPEC, ILP>(m, [&](int d) { return q[d]; }, fr, st);
+    lnew = gf_point_lnprob<SPEC, ILP, LANES>(m, [&](int d) { return q[d]; }, fr, st, lane);
     const double diff = dr.lz + lnew - lold;
     GF_STAGE(10);
     return diff > dr.lu;
 }
 
 /* one stretch-move update of walker k (in half h) of chain c, positions in global memory */
-template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
-GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int h, int64_t step) {
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1>
+GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int h, int64_t step, int lane = 0) {
     const int ndim = m.ndim, half = A.nwalkers / 2;
     const uint64_t gid = (uint64_t)(A.chain0 + c) * (uint64_t)A.nwalkers + (uint64_t)k;
     gf_ens_draw dr = gf_ens_draws(A, gid, step, half);
@@ -124,14 +131,14 @@ GF_HD unsigned gf_ens_update(const gf_dev_model& m, const gf_ens_args& A, int64_
     double lnew;
     /* positions of other walkers were written by other SMs before the last grid barrier: read them
      * through L2 (ld.global.cg), not through this SM's non-coherent L1 */
-    const bool accept = gf_ens_move<SPEC, ILP, false>(
-        m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew);
-    if (accept) {
+    const bool accept = gf_ens_move<SPEC, ILP, false, LANES>(
+        m, A, dr, [&](int d) { return GF_LDCG(cj + d); }, [&](int d) { return GF_LDCG(p + d); }, GF_LDCG(A.lnp + c * A.nwalkers + k), q, lnew, lane);
+    if (accept && lane == 0) { /* with two lanes per walker both hold the same proposal and decision: one writes */
         _Pragma("unroll") for (int d = 0; d < (GF_SPEC_STATIC_NDIM(SPEC) > 0 ? GF_SPEC_STATIC_NDIM(SPEC) : GF_MAX_DIM); ++d)
                         if (d < ndim) p[d] = q[d]; /* static indices keep q in registers */
         A.lnp[c * A.nwalkers + k] = lnew;
     }
-    return accept ? 1u : 0u;
+    return (accept && lane == 0) ? 1u : 0u;
 }
 
 GF_HD void gf_ens_store(const gf_dev_model& m, const gf_ens_args& A, int64_t c, int k, int64_t slot, int64_t nstore) {

@@ -194,30 +194,40 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * renormalisation and are not applied per bin.
  */
 /* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (deflation
- * fallback), the transition in its four independent entries and the width-weighted sums. */
-template <int ILP, class TPART>
+ * fallback), the transition in its four independent entries and the width-weighted sums.
+ *
+ * LANES = 1: one thread runs all bins of its point in increasing order (log-posterior kernel, scans, evidence).
+ * LANES = 2 (device-resident sampler): the two adjacent lanes 2w, 2w+1 of a warp evaluate ONE point together; lane
+ * `lane` (= threadIdx.x & 1) runs the bins of its own parity in increasing order, and the two partial sums are
+ * exchanged with one __shfl_xor_sync each -- addition commutes, so both lanes hold the same bits afterwards and take
+ * the same accept / reject decision.  Every launch shape of the sampler uses the same split, hence identical chains.
+ * The sampler is bound by the latency of one thread's instruction stream (gf_ensemble.cu); halving the bin work per
+ * thread shortens that stream by ~40 %. */
+template <int ILP, int LANES, class TPART>
 GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
-                           double lam, double s2, double sd0, double sd1, double inv_norm, double S, double* fr) {
+                           double lam, double s2, double sd0, double sd1, double inv_norm, double S, double* fr, int lane = 0) {
+    static_assert(LANES == 1 || LANES == 2, "one thread or a pair of lanes per point");
     unsigned st = 0u;
     double a0 = 0.0, a1 = 0.0;
     /* ILP bins per iteration, i.e. ILP independent fast-path chains in flight per thread.  2: +10 % on
      * k_lnprob, which is bound by the latency of that chain at 16 warps per SM; 1: kernels whose extra
-     * per-thread state would make the second chain spill; 4: the ensemble sampler, where a single warp
-     * per SM sub-partition runs the chain and latency is all that matters */
-    int b = 0;
+     * per-thread state would make the second chain spill; 4-5: the ensemble sampler, where one or two warps
+     * per SM sub-partition run the chain and latency is all that matters */
+    constexpr int STEP = LANES;
+    int b = LANES == 2 ? lane : 0;
     if (ILP > 1) {
-        for (; b + ILP <= m.nbins; b += ILP) {
+        for (; b + STEP * (ILP - 1) < m.nbins; b += STEP * ILP) {
             gfp_x4 x[ILP];
             bool ok = true;
 #pragma unroll
-            for (int i = 0; i < ILP; ++i) ok = gfp_pencil_x4_fast(pp, pt, lam * m.g[b + i], x[i]) && ok;
+            for (int i = 0; i < ILP; ++i) ok = gfp_pencil_x4_fast(pp, pt, lam * m.g[b + STEP * i], x[i]) && ok;
             if (!ok) { /* rare: refine whichever bin failed (re-tested: the flags are not kept in registers) */
 #pragma unroll
                 for (int i = 0; i < ILP; ++i) {
                     gfp_x4 again;
-                    if (!gfp_pencil_x4_fast(pp, pt, lam * m.g[b + i], again)) {
+                    if (!gfp_pencil_x4_fast(pp, pt, lam * m.g[b + STEP * i], again)) {
                         gfp_x4 slow; /* a separate object keeps x[] in registers */
-                        st |= gfp_pencil_x4_refine(&h0, &T, lam * m.g[b + i], &slow);
+                        st |= gfp_pencil_x4_refine(&h0, &T, lam * m.g[b + STEP * i], &slow);
                         x[i] = slow;
                     }
                 }
@@ -226,13 +236,13 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
             for (int i = 0; i < ILP; ++i) {
                 double f0, f1;
                 gfp_mix4(x[i], s2, sd0, sd1, S, f0, f1);
-                const double wd = m.width[b + i];
+                const double wd = m.width[b + STEP * i];
                 a0 = fma(wd, f0, a0);
                 a1 = fma(wd, f1, a1);
             }
         }
     }
-    for (; b < m.nbins; ++b) { /* ILP = 1, or the remaining bins */
+    for (; b < m.nbins; b += STEP) { /* ILP = 1, or the remaining bins */
         const double rho = lam * m.g[b];
         gfp_x4 x;
         if (!gfp_pencil_x4_fast(pp, pt, rho, x)) {
@@ -246,6 +256,16 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
         a0 = fma(wd, f0, a0);
         a1 = fma(wd, f1, a1);
     }
+#ifdef __CUDA_ARCH__
+    if (LANES == 2) {
+        /* the mask names just the two lanes of the pair (lane == threadIdx.x & 1 by contract): they follow the same
+         * control flow up to here -- other pairs of the warp may have left early (out-of-prior proposal) */
+        const unsigned mask = 3u << (((unsigned)threadIdx.x & 31u) & ~1u);
+        a0 += __shfl_xor_sync(mask, a0, 1);
+        a1 += __shfl_xor_sync(mask, a1, 1);
+        st |= __shfl_xor_sync(mask, st, 1);
+    }
+#endif
     /* sum_b f_b = S in every bin, so the normalisation of fr.py:455-457 is inv_norm = 1 / (S sum(width)) */
     fr[0] = a0 * inv_norm;
     fr[1] = a1 * inv_norm;
@@ -253,8 +273,8 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
     return st;
 }
 
-template <int SPEC = GF_SPEC_GENERIC, int ILP = 1>
-GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr) {
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1>
+GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr, int lane = 0) {
     unsigned st = 0u;
     if (GF_SPEC_IS_SM(SPEC) || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
         double X[9];
@@ -284,7 +304,7 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
             gfp_herm3 T = m.T;
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
             GF_STAGE(7);
-            st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            st = gf_bin_loop<ILP, LANES>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
             GF_STAGE(8);
         } else {
             gfp_herm3 T;
@@ -297,10 +317,10 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr)
             const gfp_pencil_T pt = gfp_make_pencil_T(T);
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) ? gfp_adj_tf(pt.te, T) : m.adjT);
             if (GF_SPEC_IS_NPFREE(SPEC)) {
-                st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+                st = gf_bin_loop<ILP, LANES>(m, pp, pt, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
             } else {
                 const double S = q.src[0] + q.src[1] + q.src[2];
-                st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], gfp_rcp(S * m.wsum), S, fr);
+                st = gf_bin_loop<ILP, LANES>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], gfp_rcp(S * m.wsum), S, fr, lane);
             }
         }
         /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
@@ -337,7 +357,7 @@ GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, 
         const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
         for (int s = 0; s < ns; ++s) {
             double fr[3];
-            const unsigned st = gf_bin_loop<ILP>(m, pp, m.penT, h0, T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, m.penT, h0, T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
             finish(s, st, fr);
         }
     } else {
@@ -358,7 +378,7 @@ GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, 
         const double inv_norm = fixed_src ? m.inv_S_wsum : gfp_rcp(S * m.wsum);
         for (int s = 0; s < ns; ++s) {
             double fr[3];
-            const unsigned st = gf_bin_loop<ILP>(m, pp, pt, h0, T, lam_of(s), s2, sd0, sd1, inv_norm, S, fr);
+            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, pt, h0, T, lam_of(s), s2, sd0, sd1, inv_norm, S, fr);
             finish(s, st, fr);
         }
     }
@@ -439,8 +459,8 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 }
 
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
-template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, class Get>
-GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st) {
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class Get>
+GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st, int lane = 0) {
     const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC)>(m, get);
     GF_STAGE(3);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
@@ -450,7 +470,7 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
     }
     gf_point q;
     gf_resolve_point<SPEC>(m, get, q);
-    st = gf_point_fr<SPEC, ILP>(m, q, fr);
+    st = gf_point_fr<SPEC, ILP, LANES>(m, q, fr, lane);
     /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
     if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
     const double out = lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);
