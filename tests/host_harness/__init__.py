@@ -130,3 +130,11 @@ def fr_scales(fm, theta, scales):
     out, st = np.empty((n, ns, 3)), np.empty((n, ns), dtype=np.uint8)
     _lib.check(load().hh_fr_scales(fm.ref, _p(th), C.c_int64(n), _p(sc), C.c_int(ns), _p(out), _p(st)))
     return out, st
+
+
+def ndtri(p):
+    """gf_ndtri_table: (z, covered) of the table-based inverse normal CDF."""
+    p = np.ascontiguousarray(p, dtype=np.float64).ravel()
+    z, ok = np.empty_like(p), np.empty(p.shape[0], dtype=np.uint8)
+    load().hh_ndtri(_p(p), C.c_int64(p.shape[0]), _p(z), _p(ok))
+    return z, ok.astype(bool)

@@ -165,3 +165,12 @@ extern "C" int hh_fr_scales(const gf_model* model, const double* theta, int64_t 
     }
     return 0;
 }
+
+/* the table-based inverse normal CDF of the prior draws: z[i] and whether the table covered p[i] */
+extern "C" void hh_ndtri(const double* p, int64_t n, double* z, uint8_t* covered) {
+    for (int64_t i = 0; i < n; ++i) {
+        double v = NAN;
+        covered[i] = gf_ndtri_table(p[i], &v) ? 1 : 0;
+        z[i] = v;
+    }
+}

@@ -577,3 +577,42 @@ def test_get_limit_matches_reference_fixture(golden):
     assert nlim >= 10
     ev = {6: np.column_stack([g['scales_0'], g['stat_0']])}
     assert sens.limits(ev)[6] == sens.get_limit(g['scales_0'], g['stat_0'])
+
+
+def test_harness_inverse_normal_cdf_table_against_scipy():
+    """The table-based Phi^-1 of the truncated-Gaussian prior draws (csrc/gf_ndtri_table.h, gf_scan_dev.cuh) against
+    scipy.special.ndtri: 1e-13 absolute wherever the table applies (min(p, 1-p) in [2^-17, 1/2)), and it declines
+    everything else (deep tails, p = 1/2, p outside (0, 1), NaN) so that the library routine takes over."""
+    from scipy.special import ndtri
+    rng = np.random.default_rng(5)
+    p = np.concatenate([rng.uniform(0, 1, 200000), 2.0 ** -rng.uniform(1, 17, 50000), 1 - 2.0 ** -rng.uniform(1, 17, 50000),
+                        np.nextafter(2.0 ** -np.arange(1, 18), 0), 2.0 ** -np.arange(2, 18), [0.5 - 1e-17, np.nextafter(0.5, 0), np.nextafter(0.5, 1)]])
+    z, ok = hh.ndtri(p)
+    t = np.minimum(p, 1 - p)
+    assert np.array_equal(ok, (t >= 2.0 ** -17) & (t < 0.5))
+    assert ok.mean() > 0.99
+    assert np.abs(z[ok] - ndtri(p[ok])).max() < 1e-13
+    for bad in (0.5, 0.0, 1.0, -0.1, 1.1, 1e-6, 1 - 1e-6, np.nan, np.inf):
+        assert not hh.ndtri([bad])[1][0], bad
+    # exact antisymmetry (1 - q is exact for multiples of 2^-40) and monotonicity across the row boundaries
+    q = rng.integers(1 << 24, 1 << 39, 100000).astype(np.float64) * 2.0 ** -40
+    assert np.array_equal(hh.ndtri(q)[0], -hh.ndtri(1 - q)[0])
+    edges = (2.0 ** -np.arange(2, 18)[:, None] * (1 + np.arange(8) / 8)).ravel()
+    grid = np.sort(np.concatenate([q, edges, np.nextafter(edges, 0), np.nextafter(edges, 1)]))
+    zz, cov = hh.ndtri(grid)
+    assert np.all(np.diff(zz[cov]) >= -2e-13)
+    # a scan model with LIMITEDGAUSS / GAUSSIAN priors now draws on the host as well (away from the deep tails)
+    fm = scan.scan_model('texture')
+    th = hh.draw(fm, 26, 0, 2000)
+    ps = scan.scan_paramset('texture', 6)
+    from scipy.stats import norm
+    for k, prm in enumerate(ps):
+        u = go.philox_uniforms(26, 0, 2000, block=k // 4)[:, k % 4]
+        lo, hi_ = prm.ranges
+        if prm.prior.name == 'UNIFORM':
+            ref = lo + u * (hi_ - lo)
+        else:
+            a, b = norm.cdf((lo - prm.nominal_value) / prm.std), norm.cdf((hi_ - prm.nominal_value) / prm.std)
+            ref = np.clip(prm.nominal_value + prm.std * ndtri(a + u * (b - a)), lo, hi_)
+        good = np.isfinite(th[:, k])
+        assert good.mean() > 0.999 and np.max(np.abs(th[good, k] - ref[good]) / np.abs(ref[good])) < 1e-12
