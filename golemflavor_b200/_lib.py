@@ -81,6 +81,7 @@ _SIGNATURES = {
     'gf_launch_count': (C.c_uint64, []),
     'gf_device_info': (C.c_int, [C.POINTER(C.c_int32)] * 4),
     'gf_host_alloc': (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
+    'gf_host_alloc_wc': (C.c_int, [C.POINTER(C.c_void_p), C.c_uint64]),
     'gf_host_free': (C.c_int, [_P]),
     'gf_model_check': (C.c_int, [C.POINTER(Model)]),
     'gf_angles_to_u': (C.c_int, [_P, C.c_int64, _P, _P]),
@@ -215,3 +216,24 @@ def device_info():
     v = [C.c_int32() for _ in range(4)]
     check(lib.gf_device_info(*[C.byref(x) for x in v]))
     return dict(sm_count=v[0].value, cc=(v[1].value, v[2].value), clock_khz=v[3].value)
+
+
+class HostBuffer(object):
+    """Page-locked host memory from the library (``gf_host_alloc`` / ``gf_host_alloc_wc``) as a NumPy array
+    (``.array``); freed with the object.  ``write_combined=True`` is meant for input buffers the host only writes."""
+
+    def __init__(self, shape, dtype=np.float64, write_combined=False):
+        lib = load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self._ptr = C.c_void_p()
+        check((lib.gf_host_alloc_wc if write_combined else lib.gf_host_alloc)(C.byref(self._ptr), self.nbytes))
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                load().gf_host_free(self._ptr)
+                self._ptr = None
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass

@@ -65,6 +65,12 @@ extern "C" int gf_host_alloc(void** h_ptr, uint64_t bytes) {
     return GF_OK;
 }
 
+extern "C" int gf_host_alloc_wc(void** h_ptr, uint64_t bytes) {
+    GF_REQUIRE(h_ptr != nullptr, "gf_host_alloc_wc: null output pointer");
+    GF_CUDA(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
+    return GF_OK;
+}
+
 extern "C" int gf_host_free(void* h_ptr) {
     if (h_ptr) GF_CUDA(cudaFreeHost(h_ptr));
     return GF_OK;

@@ -134,6 +134,9 @@ int gf_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int3
 /* Page-locked host buffers for the *_host calls (pageable buffers work too, through an internal
  * pinned staging ring, at memcpy speed). */
 int gf_host_alloc(void** h_ptr, uint64_t bytes);
+/* The same, write-combined: for INPUT buffers the host only writes (theta): the DMA engine reads them without snooping
+ * the CPU caches, which matters when several GPUs pull from one host; host reads of such memory are slow. */
+int gf_host_alloc_wc(void** h_ptr, uint64_t bytes);
 int gf_host_free(void* h_ptr);
 /* Validate a model without launching anything (same checks as every compute call). */
 int gf_model_check(const gf_model* model);

@@ -14,7 +14,13 @@ g = np.load(os.path.join(ROOT, 'tests', 'golden', 'ref_llh.npz'))
 args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
 fn = llh.LnProb(args, asimov, pset)
 n = 1 << 22
-th = torch.as_tensor(models.draw_in_ranges(pset, n, np.random.default_rng(25 + rank))).pin_memory()
+from golemflavor_b200 import _lib
+if os.environ.get('E2E_WC', '0') == '1':   # theta in write-combined pinned memory from the library
+    hb = _lib.HostBuffer((n, 7), write_combined=True)
+    hb.array[...] = models.draw_in_ranges(pset, n, np.random.default_rng(25 + rank))
+    th = torch.from_numpy(hb.array)
+else:
+    th = torch.as_tensor(models.draw_in_ranges(pset, n, np.random.default_rng(25 + rank))).pin_memory()
 out = torch.empty(n, dtype=torch.float64).pin_memory()
 dev = torch.empty_like(th, device='cuda')
 def barrier():
@@ -41,6 +47,6 @@ for rep in range(3):
     link = 10 * n * 56 / (e0.elapsed_time(e1) * 1e-3) / 1e9
 pipe, links = gather(max(res)), gather(link)
 if rank == 0:
-    print('slots %s chunk 2^%s world %d: pipeline h2d GB/s per rank min %.1f mean %.1f | concurrent plain copy min %.1f mean %.1f | ratio of means %.3f' % (
-        os.environ.get('GF_HOST_SLOTS', '3'), os.environ.get('GF_HOST_CHUNK_LOG2', '18'), world, min(pipe), np.mean(pipe), min(links), np.mean(links), np.mean(pipe) / np.mean(links)), flush=True)
+    print('wc %s slots %s chunk 2^%s world %d: pipeline h2d GB/s per rank min %.1f mean %.1f | concurrent plain copy min %.1f mean %.1f | ratio of means %.3f' % (
+        os.environ.get('E2E_WC', '0'), os.environ.get('GF_HOST_SLOTS', '3'), os.environ.get('GF_HOST_CHUNK_LOG2', '18'), world, min(pipe), np.mean(pipe), min(links), np.mean(links), np.mean(pipe) / np.mean(links)), flush=True)
 if world > 1: dist.destroy_process_group()
