@@ -301,10 +301,11 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr,
 #endif
         GF_STAGE(6);
         if (GF_SPEC_IS_FIXED(SPEC)) {
-            gfp_herm3 T = m.T;
+            /* the fixed texture is read where it lives -- the kernel parameter (constant bank; the address of a
+             * __grid_constant__ parameter may be taken) -- by the rare refinement path: no per-point copy in local memory */
             const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
             GF_STAGE(7);
-            st = gf_bin_loop<ILP, LANES>(m, pp, m.penT, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
+            st = gf_bin_loop<ILP, LANES>(m, pp, m.penT, h0, m.T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
             GF_STAGE(8);
         } else {
             gfp_herm3 T;
@@ -353,11 +354,10 @@ GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, 
         emit(s, fr, st);
     };
     if (GF_SPEC_IS_FIXED(SPEC)) {
-        gfp_herm3 T = m.T;
         const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
         for (int s = 0; s < ns; ++s) {
             double fr[3];
-            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, m.penT, h0, T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, m.penT, h0, m.T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
             finish(s, st, fr);
         }
     } else {

@@ -199,10 +199,24 @@ extern "C" int gf_scan_samples(const gf_model* model, const gf_scan_config* cfg,
 
 /* ------------------------------------------------------------------ coverage region (plot.py:372-384) */
 
-/* out[0] += sum of counts > c, out[1] += #cells with count == c, out[2] = max count, out[3] += total,
- * out[4] += #cells with count > c */
-__global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long c,
-                                                    unsigned long long* __restrict__ out) {
+/*
+ * Sorted by content, a cell is inside the region while the inclusive cumulative sum stays below need = coverage * total
+ * (np.searchsorted(cumsum, coverage), plot.py:380-382).  With G(c) = sum of the counts > c, the content of the first
+ * excluded cell is c* = min{c : G(c) < need}: a bisection on c with one multi-block reduction per probe.  The whole
+ * search runs ON THE DEVICE -- the bisection state lives in a small stream-ordered workspace, every probe is a
+ * (reduce, decide) pair of launches without a host round trip -- and only the three result numbers are read back at the end.
+ *
+ * ws[0] gt   : sum of counts > probe          ws[4] ngt : #cells > probe         ws[8]  probe   ws[11] take
+ * ws[1] eq   : #cells == probe                ws[5] lo                           ws[9]  phase   ws[12] n_gt
+ * ws[2] max  : largest count                  ws[6] hi                           ws[10] cstar
+ * ws[3] tot  : sum of all counts              ws[7] (unused)
+ */
+enum { COV_GT = 0, COV_EQ = 1, COV_MAX = 2, COV_TOT = 3, COV_NGT = 4, COV_LO = 5, COV_HI = 6, COV_PROBE = 8, COV_PHASE = 9, COV_CSTAR = 10,
+       COV_TAKE = 11, COV_NGT_FINAL = 12, COV_WORDS = 16 };
+
+__global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long* __restrict__ ws) {
+    const unsigned long long c = ws[COV_PROBE];
+    if (ws[COV_PHASE] == 3ull) return; /* search finished: the remaining probes of the fixed-length schedule are no-ops */
     unsigned long long gt = 0ull, eq = 0ull, mx = 0ull, tot = 0ull, ngt = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long v = hist[i];
@@ -221,33 +235,78 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __
         mx = other > mx ? other : mx;
     }
     if ((threadIdx.x & 31) == 0) {
-        if (gt) atomicAdd(out, gt);
-        if (eq) atomicAdd(out + 1, eq);
-        atomicMax(out + 2, mx);
-        if (tot) atomicAdd(out + 3, tot);
-        if (ngt) atomicAdd(out + 4, ngt);
+        if (gt) atomicAdd(ws + COV_GT, gt);
+        if (eq) atomicAdd(ws + COV_EQ, eq);
+        atomicMax(ws + COV_MAX, mx);
+        if (tot) atomicAdd(ws + COV_TOT, tot);
+        if (ngt) atomicAdd(ws + COV_NGT, ngt);
     }
 }
 
-/* one block walks the cells in order: mask = count > c, plus the first `take` cells with count == c */
-__global__ void __launch_bounds__(1024) k_cov_mask(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long c,
-                                                   unsigned long long take, uint8_t* __restrict__ mask) {
+/* one thread: digest the probe that just ran, choose the next one.  phase 0: first pass (probe 0: total and maximum),
+ * 1: bisection, 2: final probe at c*, 3: done */
+__global__ void k_cov_decide(unsigned long long* __restrict__ ws, double coverage_fraction) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long phase = ws[COV_PHASE];
+    if (phase == 3ull) return;
+    const double need = coverage_fraction * (double)ws[COV_TOT];
+    const double g = (double)ws[COV_GT];
+    if (phase == 0ull) {
+        if (ws[COV_TOT] == 0ull || !(need > 0.0)) { /* empty histogram or zero coverage: nothing is masked */
+            ws[COV_CSTAR] = ws[COV_MAX];
+            ws[COV_TAKE] = 0ull;
+            ws[COV_NGT_FINAL] = 0ull;
+            ws[COV_PHASE] = 3ull;
+            return;
+        }
+        ws[COV_LO] = 0ull; /* G(0) = total >= need */
+        ws[COV_HI] = ws[COV_MAX];
+        ws[COV_PHASE] = 1ull;
+    } else if (phase == 1ull) {
+        if (g < need) ws[COV_HI] = ws[COV_PROBE]; else ws[COV_LO] = ws[COV_PROBE];
+    } else { /* phase 2: the probe was c* itself */
+        const unsigned long long cstar = ws[COV_PROBE];
+        /* tied cells j = 1, 2, ... are inside while g + j c* < need */
+        unsigned long long m = (unsigned long long)floor((need - g) / (double)cstar);
+        while (g + (double)(m + 1ull) * (double)cstar < need) ++m;
+        while (m > 0ull && !(g + (double)m * (double)cstar < need)) --m;
+        ws[COV_CSTAR] = cstar;
+        ws[COV_TAKE] = m < ws[COV_EQ] ? m : ws[COV_EQ];
+        ws[COV_NGT_FINAL] = ws[COV_NGT];
+        ws[COV_PHASE] = 3ull;
+        return;
+    }
+    const unsigned long long lo = ws[COV_LO], hi = ws[COV_HI];
+    if (hi - lo > 1ull) {
+        ws[COV_PROBE] = lo + (hi - lo) / 2ull;
+    } else {
+        ws[COV_PROBE] = hi; /* c* = hi: probe it once more for g, the tie count and the number of cells above it */
+        ws[COV_PHASE] = 2ull;
+    }
+    ws[COV_GT] = ws[COV_EQ] = ws[COV_NGT] = 0ull; /* total and maximum are kept from the first pass */
+}
+
+/* one block walks the cells in order: mask = count > c*, plus the first `take` cells with count == c* */
+__global__ void __launch_bounds__(1024) k_cov_mask(const unsigned long long* __restrict__ hist, int64_t cells, const unsigned long long* __restrict__ ws,
+                                                   uint8_t* __restrict__ mask) {
     __shared__ unsigned int warp_ties[32];
     __shared__ unsigned long long base;
+    const unsigned long long c = ws[COV_CSTAR], take = ws[COV_TAKE];
+    const bool nothing = ws[COV_NGT_FINAL] == 0ull && take == 0ull;
     if (threadIdx.x == 0) base = 0ull;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t start = 0; start < cells; start += blockDim.x) {
         const int64_t i = start + threadIdx.x;
         const unsigned long long v = i < cells ? hist[i] : 0ull;
-        const bool tie = i < cells && v == c && c > 0ull;
+        const bool tie = !nothing && i < cells && v == c && c > 0ull;
         const unsigned ballot = __ballot_sync(0xffffffffu, tie);
         if (lane == 0) warp_ties[warp] = __popc(ballot);
         __syncthreads();
         unsigned before = __popc(ballot & ((1u << lane) - 1u));
         for (int w = 0; w < warp; ++w) before += warp_ties[w];
         const unsigned long long rank = base + before; /* number of tied cells ahead of this one */
-        if (i < cells) mask[i] = (v > c || (tie && rank < take)) ? 1 : 0;
+        if (i < cells) mask[i] = (!nothing && (v > c || (tie && rank < take))) ? 1 : 0;
         __syncthreads();
         if (threadIdx.x == 0) {
             unsigned t = 0;
@@ -267,60 +326,29 @@ extern "C" int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells,
     if (int rc = gf_sm_count(&sms)) return rc;
     const int64_t want = (cells + 255) / 256;
     const unsigned blocks = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-    unsigned long long* d_out = nullptr;
-    GF_CUDA(cudaMalloc(&d_out, 5 * sizeof(unsigned long long)));
-    unsigned long long h[5] = {0, 0, 0, 0, 0};
-    /* G(c) = sum of the counts > c; one multi-block reduction per evaluation */
-    auto pass = [&](unsigned long long c) -> int {
-        GF_CUDA(cudaMemsetAsync(d_out, 0, 5 * sizeof(unsigned long long), st));
-        k_cov_reduce<<<blocks, 256, 0, st>>>(d_hist, cells, c, d_out);
-        ++g_gf_launches;
-        GF_CUDA(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
-        GF_CUDA(cudaStreamSynchronize(st));
-        return GF_OK;
-    };
-    auto finish = [&](int rc) -> int {
-        cudaFree(d_out);
-        return rc;
-    };
-    if (int rc = pass(0ull)) return finish(rc);
-    const unsigned long long total = h[3], vmax = h[2];
-    const double need = coverage_percent / 100.0 * (double)total;
-    unsigned long long cstar = vmax, take = 0ull, n_gt = 0ull;
-    if (total > 0ull && need > 0.0) {
-        /* sorted by content, a cell is inside while the inclusive cumulative sum stays < need:
-         * c* = min{c : G(c) < need} is the content of the first excluded cell; G(0) = total >= need */
-        unsigned long long lo = 0ull, hi = vmax;
-        while (hi - lo > 1ull) {
-            const unsigned long long mid = lo + (hi - lo) / 2ull;
-            if (int rc = pass(mid)) return finish(rc);
-            if ((double)h[0] < need) hi = mid; else lo = mid;
-        }
-        cstar = hi;
-        if (int rc = pass(cstar)) return finish(rc);
-        const double g = (double)h[0];
-        n_gt = h[4];
-        /* tied cells j = 1, 2, ... are inside while g + j c* < need */
-        unsigned long long m = (unsigned long long)floor((need - g) / (double)cstar);
-        while (g + (double)(m + 1ull) * (double)cstar < need) ++m;
-        while (m > 0ull && !(g + (double)m * (double)cstar < need)) --m;
-        take = m < h[1] ? m : h[1];
+    unsigned long long* ws = nullptr;
+    GF_CUDA(cudaMallocAsync(&ws, COV_WORDS * sizeof(unsigned long long), st)); /* stream-ordered: no device-wide synchronisation */
+    GF_CUDA(cudaMemsetAsync(ws, 0, COV_WORDS * sizeof(unsigned long long), st));
+    /* 1 first pass + at most 64 bisection probes (64-bit counts) + 1 final probe: a fixed schedule, probes after the end are no-ops */
+    for (int it = 0; it < 66; ++it) {
+        k_cov_reduce<<<blocks, 256, 0, st>>>(d_hist, cells, ws);
+        k_cov_decide<<<1, 32, 0, st>>>(ws, coverage_percent / 100.0);
+        g_gf_launches += 2;
     }
-    if (total > 0ull && need > 0.0) {
-        k_cov_mask<<<1, 1024, 0, st>>>(d_hist, cells, cstar, take, d_mask);
-        ++g_gf_launches;
-    } else {
-        GF_CUDA(cudaMemsetAsync(d_mask, 0, (size_t)cells, st));
-    }
+    k_cov_mask<<<1, 1024, 0, st>>>(d_hist, cells, ws, d_mask);
+    ++g_gf_launches;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return finish(gf_fail(GF_ERR_CUDA, "gf_coverage_mask: %s", cudaGetErrorString(e)));
+    unsigned long long h[COV_WORDS] = {};
+    if (e == cudaSuccess && h_info) e = cudaMemcpyAsync(h, ws, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(ws, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return gf_fail(GF_ERR_CUDA, "gf_coverage_mask: %s", cudaGetErrorString(e));
     if (h_info) {
-        h_info[0] = cstar;
-        h_info[1] = n_gt + take;
-        h_info[2] = take;
+        h_info[0] = h[COV_CSTAR];
+        h_info[1] = h[COV_NGT_FINAL] + h[COV_TAKE];
+        h_info[2] = h[COV_TAKE];
     }
-    cudaStreamSynchronize(st);
-    return finish(GF_OK);
+    return GF_OK;
 }
 
 /* ------------------------------------------------------------------ Monte-Carlo evidence */

@@ -1212,6 +1212,28 @@ def test_reference_call_variants(torch, golden):
         fn.evaluate_host(th, fr=np.empty((5, 3)))
 
 
+def test_host_pipeline_buffers_and_ring_geometry(torch, golden):
+    """gf_lnprob_host on library-allocated page-locked buffers (plain and write-combined input), on pageable memory
+    (internal staging ring) and across chunk boundaries: identical to the device path."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OET)
+    fn = llh.LnProb(args, asimov, pset)
+    n = (1 << 18) * 2 + 12345                      # two full chunks of the default ring + a ragged third
+    theta = models.draw_in_ranges(pset, n, np.random.default_rng(8))
+    ref = fn.evaluate(theta).cpu().numpy()
+    for wc in (False, True):
+        hb_in, hb_out = _lib.HostBuffer((n, fn.ndim), write_combined=wc), _lib.HostBuffer((n,))
+        hb_in.array[...] = theta
+        out = fn.evaluate_host(hb_in.array, out=hb_out.array)
+        assert out is hb_out.array and np.array_equal(out, ref, equal_nan=True)
+    frs, st = np.empty((n, 3)), np.empty(n, dtype=np.uint8)
+    out = fn.evaluate_host(theta, fr=frs, status=st)             # pageable in and out
+    assert np.array_equal(out, ref, equal_nan=True)
+    l2, f2, s2 = (x.cpu().numpy() for x in fn.evaluate(theta, want_fr=True, want_status=True))
+    assert np.array_equal(frs, f2, equal_nan=True) and np.array_equal(st, s2)
+    assert fn.evaluate_host(theta[:0]).shape == (0,)
+
+
 def test_torch_ops_equal_the_c_abi(torch, golden):
     """`torch.ops.golemflavor.*` (csrc/gf_torch_ops.cpp) against the ctypes binding of the same entry points: identical
     bits, current-stream semantics, reference-style exceptions."""
