@@ -215,8 +215,8 @@ enum { COV_GT = 0, COV_EQ = 1, COV_MAX = 2, COV_TOT = 3, COV_NGT = 4, COV_LO = 5
        COV_TAKE = 11, COV_NGT_FINAL = 12, COV_WORDS = 16 };
 
 __global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __restrict__ hist, int64_t cells, unsigned long long* __restrict__ ws) {
-    const unsigned long long c = ws[COV_PROBE];
-    if (ws[COV_PHASE] == 3ull) return; /* search finished: the remaining probes of the fixed-length schedule are no-ops */
+    const unsigned long long c = ws[COV_PROBE], phase = ws[COV_PHASE];
+    if (phase == 3ull) return; /* search finished: the remaining probes of the fixed-length schedule are no-ops */
     unsigned long long gt = 0ull, eq = 0ull, mx = 0ull, tot = 0ull, ngt = 0ull;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
         const unsigned long long v = hist[i];
@@ -237,8 +237,10 @@ __global__ void __launch_bounds__(256) k_cov_reduce(const unsigned long long* __
     if ((threadIdx.x & 31) == 0) {
         if (gt) atomicAdd(ws + COV_GT, gt);
         if (eq) atomicAdd(ws + COV_EQ, eq);
-        atomicMax(ws + COV_MAX, mx);
-        if (tot) atomicAdd(ws + COV_TOT, tot);
+        if (phase == 0ull) { /* total and maximum: first pass only (later probes would add them again) */
+            atomicMax(ws + COV_MAX, mx);
+            if (tot) atomicAdd(ws + COV_TOT, tot);
+        }
         if (ngt) atomicAdd(ws + COV_NGT, ngt);
     }
 }
