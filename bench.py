@@ -542,6 +542,16 @@ def run_gpu(opts):
                 'algorithmic_flop_per_eval': FLOP_PER_EVAL, 'algorithmic_tflops': algorithmic, 'algorithmic_ratio': algorithmic / peak if peak else None,
                 'peak_source': 'DFMA microbenchmark (gf_fp64_peak_probe) in this run; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2',
                 'hbm_gbs': hbm_gbs, 'hbm_frac': hbm_gbs / hbm_peak, 'hbm_peak_source': 'MEASURED_PEAKS.json' if peaks else 'fallback'}
+        # dispatch bound: a sub-partition dispatches one warp instruction per cycle and an fp64 instruction holds the port for
+        # two, so a warp needs >= N_fp64 + N_all cycles per point; measured = kernel time x SM clock / warps per sub-partition
+        winst = prof.get('k_lnprob_warp_inst_per_point')
+        sm_mhz = (clock_info or {}).get('sm_mhz') or _lib.device_info()['clock_khz'] / 1e3
+        if inst and winst and sm_mhz:
+            warps_per_subpartition = n / 32.0 / (_lib.device_info()['sm_count'] * 4)
+            measured_cycles = kernel_ms * 1e-3 * sm_mhz * 1e6 / warps_per_subpartition
+            roof['dispatch_bound'] = {'cycles_per_warp_point_min': inst + winst, 'cycles_per_warp_point_measured': measured_cycles,
+                                      'frac': (inst + winst) / measured_cycles, 'warp_inst_per_eval': winst,
+                                      'note': '2 x fp64 + other warp instructions (ncu, offline) against kernel time x SM clock'}
         if sustained:
             roof['sustained_seconds'] = sustained['seconds']
             roof['sustained_ms_per_step'] = sustained['ms_per_step']

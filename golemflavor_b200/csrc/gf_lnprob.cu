@@ -78,12 +78,14 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_L
         }
         double fr[3];
         unsigned st = 0u;
+        /* the rare refinement path of the bin loop re-reads the row instead of H0 / T waiting in local memory */
+        const gf_src_row again{row, LAYOUT == 0 ? th.ld_dim : (int64_t)1};
         if (KIND == GF_K_FR) {
             gf_point q;
             gf_resolve_point<SPEC>(m, get, q);
-            st = gf_point_fr<SPEC, ILP>(m, q, fr);
+            st = gf_point_fr<SPEC, ILP, 1>(m, q, fr, 0, again);
         } else {
-            lnp[i] = gf_point_lnprob<SPEC, ILP>(m, get, fr, st);
+            lnp[i] = gf_point_lnprob<SPEC, ILP, 1>(m, get, fr, st, 0, again);
         }
         if (fr_out) {
             fr_out[3 * i] = fr[0];

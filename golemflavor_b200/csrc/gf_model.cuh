@@ -10,6 +10,8 @@
 #ifndef GF_MODEL_CUH
 #define GF_MODEL_CUH
 
+#include <type_traits>
+
 #include "../../include/golemflavor_b200.h"
 #include "gf_physics.cuh"
 
@@ -193,6 +195,71 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * The source normalisation 1/sum(s) and the 1/(E_max-E_min) factor cancel in the final
  * renormalisation and are not applied per bin.
  */
+/* H0 = U diag(0, m21, m3x) U^+ (scaled by 2^70) and the new-physics matrix T = N diag(0, 1/100, 1) N^+ of one point. */
+template <int SPEC>
+GF_HD void gf_point_matrices(const gf_dev_model& m, const gf_point& q, gfp_herm3& h0, gfp_herm3& T, double& m1, double& m2) {
+    const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
+    GF_STAGE(4);
+    const gfp_cols12 u = gfp_cols_from_trig(t);
+    m1 = q.mass[0] * GFP_MASS_SCALE;
+    m2 = q.mass[1] * GFP_MASS_SCALE;
+    h0 = gfp_herm_from_cols(u, m1, m2);
+    GF_STAGE(5);
+    if (!GF_SPEC_IS_FIXED(SPEC) && (GF_SPEC_IS_NPFREE(SPEC) || m.np_free)) {
+        const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
+        T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
+    } else {
+        T = m.T;
+    }
+}
+
+/*
+ * Where the RARE refinement path of the bin loop (two eigenvalues closer than the fast path tolerates: 0.02-1.4 % of
+ * the points) gets H0 and T from.  The closed form only needs the pencil's polynomial coefficients, so a kernel that
+ * kept the two matrices around for the fallback paid 18 local-memory stores per point for them.
+ *   gf_mats_ptr     : the caller keeps both in memory (sampler, single-sample entry points: latency-bound or tiny).
+ *   gf_mats_rebuild : nothing is kept -- the fallback RECOMPUTES them from the point's theta, which the log-posterior
+ *                     kernel can always get back (it re-reads the row from global memory): a few hundred instructions
+ *                     on a path taken by < 1 % of the warps' bins.  Same functions, same inputs: the rebuilt matrices
+ *                     are the original bits.  k_lnprob: no local store left in the point loop, -0.8 %.  The scan kernels
+ *                     could re-draw the sample from its Philox counter the same way; measured, the extra live state
+ *                     (seed, index, model pointer across three call sites) made them spill and cost 2 %: they keep
+ *                     gf_mats_ptr.
+ */
+struct gf_mats_ptr {
+    const gfp_herm3* h0;
+    const gfp_herm3* T;
+};
+template <int SPEC, class ThetaSrc>
+struct gf_mats_rebuild {
+    const gf_dev_model* m;
+    ThetaSrc src; /* void operator()(const gf_dev_model&, double* theta) const */
+};
+struct gf_no_src {}; /* tag: keep the matrices in memory */
+
+/* theta of a point from a (strided) row in memory */
+struct gf_src_row {
+    const double* row;
+    int64_t ld;
+    GF_HD void operator()(const gf_dev_model& m, double* th) const {
+        for (int k = 0; k < m.ndim; ++k) th[k] = row[(int64_t)k * ld];
+    }
+};
+
+GF_HD unsigned gf_refine_bin(const gf_mats_ptr& p, double rho, gfp_x4* out) { return gfp_pencil_x4_refine(p.h0, p.T, rho, out); }
+
+template <int SPEC, class ThetaSrc>
+GF_HD_NOINLINE unsigned gf_refine_bin(const gf_mats_rebuild<SPEC, ThetaSrc> r, double rho, gfp_x4* out) {
+    double th[GF_MAX_DIM];
+    r.src(*r.m, th);
+    gf_point q;
+    gf_resolve_point<SPEC>(*r.m, [&](int k) { return th[k]; }, q);
+    gfp_herm3 h0, T;
+    double m1, m2;
+    gf_point_matrices<SPEC>(*r.m, q, h0, T, m1, m2);
+    return gfp_pencil_x4_refine(&h0, &T, rho, out);
+}
+
 /* The energy-bin loop: per bin the invariants of the pencil, the closed-form |V|^2 (deflation
  * fallback), the transition in its four independent entries and the width-weighted sums.
  *
@@ -203,8 +270,8 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
  * the same accept / reject decision.  Every launch shape of the sampler uses the same split, hence identical chains.
  * The sampler is bound by the latency of one thread's instruction stream (gf_ensemble.cu); halving the bin work per
  * thread shortens that stream by ~40 %. */
-template <int ILP, int LANES, class TPART>
-GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const gfp_herm3& h0, const gfp_herm3& T,
+template <int ILP, int LANES, class TPART, class MATS>
+GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const TPART& pt, const MATS& mats,
                            double lam, double s2, double sd0, double sd1, double inv_norm, double S, double* fr, int lane = 0) {
     static_assert(LANES == 1 || LANES == 2, "one thread or a pair of lanes per point");
     unsigned st = 0u;
@@ -227,7 +294,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
                     gfp_x4 again;
                     if (!gfp_pencil_x4_fast(pp, pt, lam * m.g[b + STEP * i], again)) {
                         gfp_x4 slow; /* a separate object keeps x[] in registers */
-                        st |= gfp_pencil_x4_refine(&h0, &T, lam * m.g[b + STEP * i], &slow);
+                        st |= gf_refine_bin(mats, lam * m.g[b + STEP * i], &slow);
                         x[i] = slow;
                     }
                 }
@@ -247,7 +314,7 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
         gfp_x4 x;
         if (!gfp_pencil_x4_fast(pp, pt, rho, x)) {
             gfp_x4 slow;
-            st |= gfp_pencil_x4_refine(&h0, &T, rho, &slow);
+            st |= gf_refine_bin(mats, rho, &slow);
             x = slow;
         }
         double f0, f1;
@@ -273,8 +340,8 @@ GF_HD unsigned gf_bin_loop(const gf_dev_model& m, const gfp_pencil_P& pp, const 
     return st;
 }
 
-template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1>
-GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr, int lane = 0) {
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class ThetaSrc = gf_no_src>
+GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr, int lane = 0, const ThetaSrc& src = ThetaSrc()) {
     unsigned st = 0u;
     if (GF_SPEC_IS_SM(SPEC) || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
         double X[9];
@@ -286,43 +353,42 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr,
         fr[1] = f[1] * inv;
         fr[2] = f[2] * inv;
     } else if (!GF_SPEC_IS_SM(SPEC)) {
-        const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
-        GF_STAGE(4);
-        const gfp_cols12 u = gfp_cols_from_trig(t);
-        /* h0 and T live in local memory for the rare Jacobi fallback; the loop itself runs on
-         * the polynomial invariants of the pencil H0 + rho T */
-        const double m1 = q.mass[0] * GFP_MASS_SCALE, m2 = q.mass[1] * GFP_MASS_SCALE;
-        gfp_herm3 h0 = gfp_herm_from_cols(u, m1, m2);
-        GF_STAGE(5);
+        /* the loop runs on the polynomial invariants of the pencil H0 + rho T; the matrices themselves are only needed
+         * by the rare refinement path (see gf_mats_ptr / gf_mats_rebuild) */
+        gfp_herm3 h0, T;
+        double m1, m2;
+        gf_point_matrices<SPEC>(m, q, h0, T, m1, m2);
 #ifdef __CUDA_ARCH__
         const double lam = exp10(q.loglam);
 #else
         const double lam = pow(10.0, q.loglam);
 #endif
         GF_STAGE(6);
-        if (GF_SPEC_IS_FIXED(SPEC)) {
+        /* gf_mats_ptr: taking the addresses parks h0 / T in local memory; gf_mats_rebuild: they die after the pencil */
+        auto run = [&](const auto& mats) {
+            if (GF_SPEC_IS_FIXED(SPEC)) {
+                const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
+                GF_STAGE(7);
+                st = gf_bin_loop<ILP, LANES>(m, pp, m.penT, mats, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
+                GF_STAGE(8);
+            } else {
+                const bool npf = GF_SPEC_IS_NPFREE(SPEC) || m.np_free;
+                const gfp_pencil_T pt = gfp_make_pencil_T(T);
+                const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, npf ? gfp_adj_tf(pt.te, T) : m.adjT);
+                if (GF_SPEC_IS_NPFREE(SPEC)) {
+                    st = gf_bin_loop<ILP, LANES>(m, pp, pt, mats, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
+                } else {
+                    const double S = q.src[0] + q.src[1] + q.src[2];
+                    st = gf_bin_loop<ILP, LANES>(m, pp, pt, mats, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], gfp_rcp(S * m.wsum), S, fr, lane);
+                }
+            }
+        };
+        if constexpr (std::is_same<ThetaSrc, gf_no_src>::value) {
             /* the fixed texture is read where it lives -- the kernel parameter (constant bank; the address of a
-             * __grid_constant__ parameter may be taken) -- by the rare refinement path: no per-point copy in local memory */
-            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
-            GF_STAGE(7);
-            st = gf_bin_loop<ILP, LANES>(m, pp, m.penT, h0, m.T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
-            GF_STAGE(8);
+             * __grid_constant__ parameter may be taken): no per-point copy */
+            run(gf_mats_ptr{&h0, GF_SPEC_IS_FIXED(SPEC) ? &m.T : &T});
         } else {
-            gfp_herm3 T;
-            if (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) {
-                const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
-                T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
-            } else {
-                T = m.T;
-            }
-            const gfp_pencil_T pt = gfp_make_pencil_T(T);
-            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, (GF_SPEC_IS_NPFREE(SPEC) || m.np_free) ? gfp_adj_tf(pt.te, T) : m.adjT);
-            if (GF_SPEC_IS_NPFREE(SPEC)) {
-                st = gf_bin_loop<ILP, LANES>(m, pp, pt, h0, T, lam, m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr, lane);
-            } else {
-                const double S = q.src[0] + q.src[1] + q.src[2];
-                st = gf_bin_loop<ILP, LANES>(m, pp, pt, h0, T, lam, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], gfp_rcp(S * m.wsum), S, fr, lane);
-            }
+            run(gf_mats_rebuild<SPEC, ThetaSrc>{&m, src});
         }
         /* |V|^2 must be doubly stochastic, hence 0 <= fr <= 1: a violation beyond epsilon is the
          * analogue of the reference's failed unitarity assertion (fr.py:489-498) */
@@ -340,47 +406,46 @@ GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr,
  * `emit(s, fr, status)` is called with the composition at lam_of(s) = 10^logLam_s for s = 0 .. ns-1.  Same arithmetic per
  * scale as gf_point_fr (which is the ns = 1 case with lam = exp10(q.loglam)).
  */
-template <int SPEC, int ILP, class LamOf, class Emit>
-GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, LamOf lam_of, Emit emit) {
+template <int SPEC, int ILP, class LamOf, class Emit, class ThetaSrc = gf_no_src>
+GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, LamOf lam_of, Emit emit, const ThetaSrc& src = ThetaSrc()) {
     static_assert(!GF_SPEC_IS_SM(SPEC), "the scale grid needs the BSM path");
-    const gfp_trig t = gfp_angles_trig(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
-    const gfp_cols12 u = gfp_cols_from_trig(t);
-    const double m1 = q.mass[0] * GFP_MASS_SCALE, m2 = q.mass[1] * GFP_MASS_SCALE;
-    gfp_herm3 h0 = gfp_herm_from_cols(u, m1, m2);
+    gfp_herm3 h0, T;
+    double m1, m2;
+    gf_point_matrices<SPEC>(m, q, h0, T, m1, m2);
     auto finish = [&](int s, unsigned st, double* fr) {
         const double mn = fmin(fr[0], fmin(fr[1], fr[2]));
         if (!(mn >= -m.epsilon)) st |= GFP_ST_NON_UNITARY;
         if (!(fabs(fr[0]) + fabs(fr[1]) + fabs(fr[2]) < 1e300)) st |= GFP_ST_NON_FINITE;
         emit(s, fr, st);
     };
-    if (GF_SPEC_IS_FIXED(SPEC)) {
-        const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
-        for (int s = 0; s < ns; ++s) {
-            double fr[3];
-            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, m.penT, h0, m.T, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
-            finish(s, st, fr);
-        }
-    } else {
-        gfp_herm3 T;
-        const bool npf = GF_SPEC_IS_NPFREE(SPEC) || m.np_free;
-        if (npf) {
-            const gfp_trig tn = gfp_angles_trig(q.np[0], q.np[1], q.np[2], q.np[3]);
-            T = gfp_herm_from_cols(gfp_cols_from_trig(tn), GFP_T_EIG1, GFP_T_EIG2);
+    auto run = [&](const auto& mats) {
+        if (GF_SPEC_IS_FIXED(SPEC)) {
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, m.T, m.penT.te, m.adjT);
+            for (int s = 0; s < ns; ++s) {
+                double fr[3];
+                const unsigned st = gf_bin_loop<ILP, 1>(m, pp, m.penT, mats, lam_of(s), m.fixed_src[2], m.src_sd0, m.src_sd1, m.inv_S_wsum, m.src_S, fr);
+                finish(s, st, fr);
+            }
         } else {
-            T = m.T;
+            const bool npf = GF_SPEC_IS_NPFREE(SPEC) || m.np_free;
+            const gfp_pencil_T pt = gfp_make_pencil_T(T);
+            const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, npf ? gfp_adj_tf(pt.te, T) : m.adjT);
+            const bool fixed_src = GF_SPEC_IS_NPFREE(SPEC) || gf_model_has_fixed_source(m);
+            const double S = fixed_src ? m.src_S : q.src[0] + q.src[1] + q.src[2];
+            const double s2 = fixed_src ? m.fixed_src[2] : q.src[2];
+            const double sd0 = fixed_src ? m.src_sd0 : q.src[0] - q.src[2], sd1 = fixed_src ? m.src_sd1 : q.src[1] - q.src[2];
+            const double inv_norm = fixed_src ? m.inv_S_wsum : gfp_rcp(S * m.wsum);
+            for (int s = 0; s < ns; ++s) {
+                double fr[3];
+                const unsigned st = gf_bin_loop<ILP, 1>(m, pp, pt, mats, lam_of(s), s2, sd0, sd1, inv_norm, S, fr);
+                finish(s, st, fr);
+            }
         }
-        const gfp_pencil_T pt = gfp_make_pencil_T(T);
-        const gfp_pencil_P pp = gfp_make_pencil_P(h0, m1, m2, T, pt.te, npf ? gfp_adj_tf(pt.te, T) : m.adjT);
-        const bool fixed_src = GF_SPEC_IS_NPFREE(SPEC) || gf_model_has_fixed_source(m);
-        const double S = fixed_src ? m.src_S : q.src[0] + q.src[1] + q.src[2];
-        const double s2 = fixed_src ? m.fixed_src[2] : q.src[2];
-        const double sd0 = fixed_src ? m.src_sd0 : q.src[0] - q.src[2], sd1 = fixed_src ? m.src_sd1 : q.src[1] - q.src[2];
-        const double inv_norm = fixed_src ? m.inv_S_wsum : gfp_rcp(S * m.wsum);
-        for (int s = 0; s < ns; ++s) {
-            double fr[3];
-            const unsigned st = gf_bin_loop<ILP, 1>(m, pp, pt, h0, T, lam_of(s), s2, sd0, sd1, inv_norm, S, fr);
-            finish(s, st, fr);
-        }
+    };
+    if constexpr (std::is_same<ThetaSrc, gf_no_src>::value) {
+        run(gf_mats_ptr{&h0, GF_SPEC_IS_FIXED(SPEC) ? &m.T : &T});
+    } else {
+        run(gf_mats_rebuild<SPEC, ThetaSrc>{&m, src});
     }
 }
 
@@ -459,8 +524,8 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 }
 
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
-template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class Get>
-GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st, int lane = 0) {
+template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class Get, class ThetaSrc = gf_no_src>
+GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st, int lane = 0, const ThetaSrc& src = ThetaSrc()) {
     const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC)>(m, get);
     GF_STAGE(3);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
@@ -470,7 +535,7 @@ GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigne
     }
     gf_point q;
     gf_resolve_point<SPEC>(m, get, q);
-    st = gf_point_fr<SPEC, ILP, LANES>(m, q, fr, lane);
+    st = gf_point_fr<SPEC, ILP, LANES>(m, q, fr, lane, src);
     /* scripts/mc_*.py triangle_llh: parameters are only stored, "return 1. # Flat LLH" */
     if (m.llh_kind == GF_LLH_FLAT) return lp + m.llh_const;
     const double out = lp + gf_multi_gaussian(fr, m.fr_bf, m.half_inv_s2, m.lognorm3, m.offset, m.emulate_underflow, m.underflow_logpdf);

@@ -110,6 +110,8 @@ def capture(tag, name, rep, traffic_key=None, points=0):
         fp = out.get('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed')
         if fp:
             t[traffic_key.replace('bytes_per_launch', 'fp64_pipe_pct')] = fp['value']
+        if points and 'smsp__inst_executed.sum' in out:
+            t[traffic_key.replace('bytes_per_launch', 'warp_inst_per_point')] = out['smsp__inst_executed.sum']['value'] / (points / 32.0)
         inst = fp64_thread_inst(out)
         if inst and points:
             t[traffic_key.replace('bytes_per_launch', 'fp64_thread_inst_per_point')] = inst / points

@@ -36,11 +36,13 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def lnprob(fm, theta, spec=-1):
+def lnprob(fm, theta, spec=-1, rebuild=False):
+    """rebuild=True: the refinement path recomputes H0 / T from the row (k_lnprob) instead of keeping them in memory."""
     th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
     n = th.shape[0]
     lnp, fr, st = np.empty(n), np.empty((n, 3)), np.empty(n, dtype=np.uint8)
-    rc = load().hh_lnprob(fm.ref, _p(th), C.c_int64(n), _p(lnp), _p(fr), _p(st), C.c_int(spec))
+    fn = load().hh_lnprob_rebuild if rebuild else load().hh_lnprob
+    rc = fn(fm.ref, _p(th), C.c_int64(n), _p(lnp), _p(fr), _p(st), C.c_int(spec))
     _lib.check(rc)
     return lnp, fr, st
 

@@ -174,3 +174,21 @@ extern "C" void hh_ndtri(const double* p, int64_t n, double* z, uint8_t* covered
         z[i] = v;
     }
 }
+
+/* the log-posterior with the refinement path REBUILDING H0 / T from the row (as k_lnprob does) instead of keeping them */
+extern "C" int hh_lnprob_rebuild(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st, int spec) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    const bool fixed = use_fixed(d, spec);
+    for (int64_t i = 0; i < n; ++i) {
+        const double* row = theta + i * d.ndim;
+        auto get = [&](int k) { return row[k]; };
+        const gf_src_row again{row, 1};
+        unsigned s = 0u;
+        double f[3];
+        lnp[i] = fixed ? gf_point_lnprob<GF_SPEC_FIXED, 2, 1>(d, get, f, s, 0, again) : gf_point_lnprob<GF_SPEC_GENERIC, 2, 1>(d, get, f, s, 0, again);
+        if (fr) memcpy(fr + 3 * i, f, sizeof(f));
+        if (st) st[i] = (uint8_t)s;
+    }
+    return 0;
+}

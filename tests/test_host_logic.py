@@ -616,3 +616,26 @@ def test_harness_inverse_normal_cdf_table_against_scipy():
             ref = np.clip(prm.nominal_value + prm.std * ndtri(a + u * (b - a)), lo, hi_)
         good = np.isfinite(th[:, k])
         assert good.mean() > 0.999 and np.max(np.abs(th[good, k] - ref[good]) / np.abs(ref[good])) < 1e-12
+
+
+def test_harness_refinement_rebuilds_identical_matrices(golden):
+    """k_lnprob keeps neither H0 nor T for the rare refinement path: it re-reads the row and rebuilds them
+    (gf_mats_rebuild).  Same bits as the variant that keeps them in memory, on a batch with refined points, for the
+    fixed-texture, the free-NP and the sampled-source specialisations."""
+    g = golden('ref_llh.npz')
+    rng = np.random.default_rng(12)
+    cases = [models.bsm_model_c3(g['asimov_angles'], dim=3, texture=Texture.OET),
+             models.bsm_model_c3(g['asimov_angles'], dim=6, texture=Texture.OUT),
+             models.bsm_sampled_source(g['asimov_angles'], 'angles', 6, Texture.OET)]
+    a11 = models.bsm_args(6, Texture.NONE)
+    a11.injected_ratio, a11.smearing = [1 / 3, 1 / 3, 1 / 3], 0.02
+    cases.append((a11, None, models.bsm11_paramset(6)))
+    refined = 0
+    for args, asimov, pset in cases:
+        fm = model.flatten(args, asimov, pset)
+        theta = models.draw_in_ranges(pset, 40000, rng)
+        l0, f0, s0 = hh.lnprob(fm, theta)
+        l1, f1, s1 = hh.lnprob(fm, theta, rebuild=True)
+        assert np.array_equal(l0, l1, equal_nan=True) and np.array_equal(f0, f1, equal_nan=True) and np.array_equal(s0, s1)
+        refined += int(np.count_nonzero(s0 & _lib.ST_REFINED))
+    assert refined > 20
