@@ -489,7 +489,7 @@ def run_gpu(opts):
         p3 = mcmc.flat_seed(pset, 4096)
         smp3 = mcmc.DeviceEnsembleSampler(4096, fn.ndim, fn, seed=25)
         smp3.run_mcmc(p3, 100, store=False)
-        sec, _ = timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))
+        sec = min(timed(lambda: smp3.run_mcmc(None, 2000, store=False, return_tensor=True))[0] for _ in range(2))   # best of two launches
         info['c3_bsm_4096_walkers_us_per_step'] = sec / 2000 * 1e6
         info['c3_acceptance'] = float(np.mean(smp3.acceptance_fraction))
         sens.sweep(segments=100, nwalkers=60, burnin=5, nsteps=5)   # warm-up (first launches, NCCL float64 path)

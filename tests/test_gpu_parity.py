@@ -1135,6 +1135,12 @@ def test_evidence_grid_kernel_against_per_scale_launches_and_oracle(torch):
                 assert abs(got[k] - ref) < 1e-9 * abs(ref), (dim, sc, got[k], ref)
         parts = [scan.scan_evidence_grid(fm, scales, c, seed=26, first_index=s, distributed=False) + np.log(c) for s, c in ((0, 11000), (11000, 19000))]
         assert np.max(np.abs(np.logaddexp(parts[0], parts[1]) - np.log(n) - got) / np.abs(got)) < 1e-12
+    # degenerate shapes: one scale is the single-scale entry point; no samples -> -inf; fewer samples than threads
+    fm.struct.fixed_loglam = -40.0
+    assert abs(scan.scan_evidence_grid(fm, [-40.0], 5000, seed=4, distributed=False)[0] - scan.scan_evidence(fm, 5000, seed=4, distributed=False)) < 1e-12 * 400
+    assert np.all(np.isneginf(scan.scan_evidence_grid(fm, [-40.0, -35.0], 0, distributed=False)))
+    few = scan.scan_evidence_grid(fm, scales, 37, seed=4, distributed=False)
+    assert few.shape == (len(scales),) and np.all(np.isfinite(few))
     # sampled source (GENERIC specialisation, column-map path) + a model with a sampled scale is refused
     g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_llh.npz'))
     a9, as9, ps9 = models.bsm_sampled_source(g['asimov_angles'], 'angles', 6, Texture.OUT)
