@@ -392,10 +392,6 @@ GF_HD double gfp_tr_adj_pre(const gfp_adj3& j, const double* eb, const gfp_herm3
     return fma(2.0, off, fma(j.k0, eb[0], fma(j.k1, eb[1], j.k2 * eb[2])));
 }
 
-GF_HD double gfp_tr_adj(const double* ea, const gfp_herm3& A, const double* eb, const gfp_herm3& B) {
-    return gfp_tr_adj_pre(gfp_adj_tf(ea, A), eb, B);
-}
-
 /* Q = tr(H'^2)/6 and det(H')/2 of a Hermitian matrix with eigenvalues (0, m1, m2): they depend on the
  * spectrum alone, not on the mixing -- for H0 = U diag(0, m21, m3x) U^+ on the mass-squared differences
  * only, for T = N diag(0, 1/100, 1) N^+ they are constants of the model whatever the NP angles. */
