@@ -325,9 +325,28 @@ def run_gpu(opts):
         torch.cuda.synchronize()
         peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
 
-    # -- device-resident throughput: exactly K steps
+    # -- warm-up, then the same launch repeated for >= 1 s (sustained clocks and rate under a long load), then EXACTLY K timed steps
     for _ in range(opts.warmup):
         step()
+    sus_steps = int(max(opts.steps, np.ceil(opts.sustain_s * 1e3 / 0.55))) if opts.sustain_s > 0 else 0
+    sustained = None
+    if sus_steps:
+        clocks2 = ClockSampler(local)
+        barrier()
+        if rank == 0:
+            clocks2.start()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(sus_steps):
+            step()
+        s1.record()
+        barrier()
+        sus_ms = max_over_ranks(s0.elapsed_time(s1))
+        c2 = clocks2.stop() if rank == 0 else None
+        sustained = {'steps': sus_steps, 'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / sus_steps,
+                     'value': world * n * sus_steps / (sus_ms * 1e-3), 'clocks': c2}
+
+    # -- device-resident throughput: exactly K steps
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -345,25 +364,6 @@ def run_gpu(opts):
     clock_info = clocks.stop() if rank == 0 else None
     value = world * n * opts.steps / (ms * 1e-3)
     kernel_ms = ms / opts.steps
-
-    # -- the same launch repeated for >= 1 s (the K-step region is a burst of a few ms): sustained clocks and rate
-    sus_steps = int(max(opts.steps, np.ceil(opts.sustain_s * 1e3 / kernel_ms))) if opts.sustain_s > 0 else 0
-    sustained = None
-    if sus_steps:
-        clocks2 = ClockSampler(local)
-        barrier()
-        if rank == 0:
-            clocks2.start()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(sus_steps):
-            step()
-        s1.record()
-        barrier()
-        sus_ms = max_over_ranks(s0.elapsed_time(s1))
-        c2 = clocks2.stop() if rank == 0 else None
-        sustained = {'steps': sus_steps, 'seconds': sus_ms * 1e-3, 'ms_per_step': sus_ms / sus_steps,
-                     'value': world * n * sus_steps / (sus_ms * 1e-3), 'clocks': c2}
 
     # -- end to end through the host API
     out_host = torch.empty(n, dtype=torch.float64).pin_memory()
