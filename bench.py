@@ -25,12 +25,14 @@ the hot path over that batch = ONE kernel launch.
   config   : besides the workload, the secondary sections the driver must keep: the sharded
              Monte-Carlo scan (config 4, `scan_*`: whole-job seconds incl. the NCCL all-reduce of the
              histograms, checksum) and the sampler-shaped configs C1/C2/C3/C5 and K1 (`c*_`, `k1_*`)
-  cpu_baseline : the oracle's scalar float128 ln_prob (port of the reference path) on 1 host core for
-             the headline model, plus the config-2 notebook model and config 1 end to end on the CPU
+  cpu_baseline : the reference's scalar float128 ln_prob (baseline/_ref; the oracle port if that is absent) on
+             1 host core for the headline model, plus the config-2 notebook model and config 1 end to end on
+             the CPU (both: the oracle port)
 
-`--impl reference` times the reference's CPU algorithm (the oracle port; the reference is pure
-Python and cannot travel to the GPU box) on all host cores for the same metric and config: exactly
-K steps after W warm-up steps, each step a bounded sample of the workload.
+`--impl reference` times the reference's own CPU implementation -- the UNMODIFIED package installed in
+baseline/_ref (git-ignored, travels with the snapshot; `kind: "reference"`), else the oracle port
+(`kind: "port"`) -- on all host cores for the same metric and config: exactly K steps after W warm-up
+steps, each step a bounded sample of the workload.
 """
 
 import argparse
@@ -149,17 +151,115 @@ def _cpu_eval_chunk(job):
     return time.perf_counter() - t0, count, float(np.sum(np.isfinite(out)))
 
 
-def cpu_baseline(per_core, cores, pool=None, seed0=1000):
+# ---------------------------------------------------------------------------------------------- the reference itself
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+TEXTURE_OET = (0. + 1e-9, 0.25, 0. + 1e-9, 0. + 1e-9)      # fr.py:370-376, the OET angle tuple
+
+
+KIND_NOTE = {
+    'reference': "the UNMODIFIED reference package (baseline/_ref): llh.lnprior + fr.flux_averaged_BSMu + llh.multi_gaussian composed "
+                 "as llh.ln_prob / examples/inference.ipynb (GolemFit absent)",
+    'port': 'the oracle restatement of the same functions (baseline/_ref not installed)'}
+
+
+def _reference_problem():
+    """The UNMODIFIED reference package (`pip install --target baseline/_ref /root/reference`, git-ignored, travels to
+    the GPU box with the snapshot) set up for the headline workload, or None when it is not installed / importable.
+    Imported behind the two-line Python-3.12 shim of tests/golden/make_golden.py; nothing else is patched.  GolemFit is
+    proprietary and absent, so the likelihood is the Gaussian stand-in the reference documents
+    (examples/inference.ipynb:307-366, README.md:76-77): `llh.ln_prob` (llh.py:121-130: deep copies, `lnprior`, early
+    -inf) with `multi_gaussian(flux_averaged_BSMu(theta), injected, smearing)` in place of `gf_utils.get_llh`.  The
+    fixed texture is passed as Texture.NONE with the explicit OET angle tuple (fr.py:370-376) because the texture branch
+    builds a ragged array under NumPy >= 1.24 (same work-around as the golden fixtures): identical arithmetic."""
+    if 'ref' in _CPU_STATE:
+        return _CPU_STATE['ref']
+    _CPU_STATE['ref'] = None
+    if not os.path.isdir(os.path.join(REF_DIR, 'golemflavor')):
+        return None
+    try:
+        import collections
+        import collections.abc
+        import fractions
+        import math
+        from argparse import Namespace
+        if not hasattr(fractions, 'gcd'):
+            fractions.gcd = math.gcd                           # golemflavor/misc.py:15
+        if not hasattr(collections, 'Sequence'):
+            collections.Sequence = collections.abc.Sequence    # golemflavor/param.py:15
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):        # "Running without GolemFit"
+            import golemflavor.fr as rfr
+            import golemflavor.llh as rllh
+            from golemflavor import enums as renums
+            from golemflavor.param import Param as RParam, ParamSet as RParamSet
+    except Exception as exc:  # noqa: BLE001
+        _note('reference package in baseline/_ref not importable:', repr(exc))
+        return None
+    import models  # noqa: F401
+    (args, asimov, pset), _ = build_problem()
+
+    def conv(p, tag=None):
+        prior = getattr(renums.PriorsCateg, p.prior.name) if p.prior is not None else None
+        return RParam(name=p.name, value=p.nominal_value, seed=list(p.seed), ranges=list(p.ranges), std=p.std, prior=prior,
+                      tag=getattr(renums.ParamTag, (tag or p.tag).name))
+
+    plist = [conv(p) for p in pset]
+    scale_at = [k for k, p in enumerate(plist) if p.tag is renums.ParamTag.SCALE][0]
+    mm = [RParam(name=nm, value=v, ranges=[0., 2 * np.pi], std=0.2, tag=renums.ParamTag.MMANGLES)
+          for nm, v in zip(['np_s12', 'np_c13', 'np_s23', 'np_dcp'], TEXTURE_OET)]
+    rpset = RParamSet(plist[:scale_at] + mm + plist[scale_at:])
+    rasimov = RParamSet([conv(p) for p in asimov])
+    rargs = Namespace(binning=np.asarray(args.binning), source_ratio=rfr.normalize_fr(args.source_ratio), dimension=args.dimension,
+                      texture=renums.Texture.NONE, no_bsm=False)
+    smearing = rasimov[0].std
+    injected = rfr.angles_to_fr(rasimov.from_tag(renums.ParamTag.BESTFIT, values=True))
+    from copy import deepcopy
+
+    def ln_prob(theta7):
+        theta = list(theta7[:scale_at]) + list(TEXTURE_OET) + list(theta7[scale_at:])
+        dc_pset = deepcopy(rpset)                    # llh.py:122-123
+        deepcopy(rasimov)
+        lp = rllh.lnprior(theta, paramset=dc_pset)
+        if not np.isfinite(lp):
+            return -np.inf
+        fr = rfr.flux_averaged_BSMu(theta, rargs, -2.0, dc_pset)
+        return lp + rllh.multi_gaussian(fr, injected, smearing)
+
+    _CPU_STATE['ref'] = (ln_prob, pset)
+    return _CPU_STATE['ref']
+
+
+def _ref_eval_chunk(job):
+    """The reference's own ln_prob composition on a chunk of the synthetic theta distribution."""
+    seed, count = job
+    ln_prob, pset = _reference_problem()
+    theta = synth_theta(pset, count, seed, sys.modules['models'])
+    t0 = time.perf_counter()
+    out = []
+    with np.errstate(all='ignore'):
+        for t in theta:
+            try:
+                out.append(float(ln_prob(t)))
+            except AssertionError:   # the reference's unitarity assertion (fr.py:493-498): same work was done
+                out.append(np.nan)
+    return time.perf_counter() - t0, count, float(np.sum(np.isfinite(out)))
+
+
+def cpu_baseline(per_core, cores, pool=None, seed0=1000, kind='port'):
+    chunk = _ref_eval_chunk if kind == 'reference' else _cpu_eval_chunk
     jobs = [(seed0 + c, per_core) for c in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
-        res = [_cpu_eval_chunk(jobs[0])]
+        res = [chunk(jobs[0])]
     elif pool is not None:
-        res = pool.map(_cpu_eval_chunk, jobs, chunksize=1)
+        res = pool.map(chunk, jobs, chunksize=1)
     else:
         import multiprocessing as mp
         with mp.get_context('fork').Pool(cores) as p:
-            res = p.map(_cpu_eval_chunk, jobs, chunksize=1)
+            res = p.map(chunk, jobs, chunksize=1)
     wall = time.perf_counter() - t0
     total = sum(r[1] for r in res)
     compute = max(r[0] for r in res)
@@ -221,25 +321,27 @@ def run_reference(opts):
     cores = os.cpu_count() or 1
     steps, warmup = max(1, opts.steps), max(0, opts.warmup)
     per_core = int(min(150, max(4, round(30.0 * 90.0 / (steps + warmup)))))   # ~90 evals/s/core
-    _cpu_problem()
+    kind = 'reference' if _reference_problem() is not None else 'port'         # set up before the fork: workers inherit it
+    if kind == 'port':
+        _cpu_problem()
     with mp.get_context('fork').Pool(cores) as pool:
         for w in range(warmup):
-            cpu_baseline(per_core, cores, pool, seed0=500000 + 1000 * w)
+            cpu_baseline(per_core, cores, pool, seed0=500000 + 1000 * w, kind=kind)
         t0 = time.perf_counter()
         total = 0
         for k in range(steps):
-            _, n, _ = cpu_baseline(per_core, cores, pool, seed0=1000 * (k + 1))
+            _, n, _ = cpu_baseline(per_core, cores, pool, seed0=1000 * (k + 1), kind=kind)
             total += n
         elapsed = time.perf_counter() - t0
     value = total / elapsed
     sample = '{0} scalar float128 ln_prob evaluations per step ({1} per process x {2} processes), same model and synthetic theta ' \
-             'distribution as the GPU arm'.format(per_core * cores, per_core, cores)
+             'distribution as the GPU arm; {3}'.format(per_core * cores, per_core, cores, KIND_NOTE[kind])
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': opts.gpus, 'steps': steps,
         'warmup': warmup, 'ms_per_step': 1e3 * elapsed / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f80 (x87 long double, as the reference)', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'sample': sample},
-        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -510,9 +612,10 @@ def run_gpu(opts):
     if rank == 0:
         base = None
         if world == 1 and opts.cpu_evals > 0:
-            v, total, wall = cpu_baseline(opts.cpu_evals, 1)
-            base = {'value': v, 'unit': 'evals/s', 'cores': 1, 'kind': 'port',
-                    'sample': '{0} scalar float128 ln_prob evaluations of the same model ({1:.1f} s)'.format(total, wall)}
+            kind = 'reference' if _reference_problem() is not None else 'port'
+            v, total, wall = cpu_baseline(opts.cpu_evals, 1, kind=kind)
+            base = {'value': v, 'unit': 'evals/s', 'cores': 1, 'kind': kind,
+                    'sample': '{0} scalar float128 ln_prob evaluations of the same model ({1:.1f} s); {2}'.format(total, wall, KIND_NOTE[kind])}
             try:
                 base['c2_notebook_model'] = cpu_baseline_c2(max(50, opts.cpu_evals // 3))
                 base['c1_end_to_end'] = cpu_baseline_c1(max(10, opts.cpu_evals // 8))

@@ -526,11 +526,41 @@ def test_bench_reference_arm_prints_one_contract_line():
                 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
         assert key in d, key
     assert d['impl'] == 'reference' and d['metric'] == 'log-posterior evals/sec' and d['value'] > 10
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    installed = os.path.isdir(os.path.join(root, 'baseline', '_ref', 'golemflavor'))
+    assert d['cpu_baseline']['kind'] == ('reference' if installed else 'port') and d['cpu_baseline']['cores'] >= 1
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     gpu = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '1'], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True, env=env, timeout=600)
     assert gpu.returncode != 0 and 'no CUDA device' in (gpu.stderr + gpu.stdout)
+
+
+def test_installed_reference_agrees_with_the_oracle_on_the_headline_model():
+    """`baseline/_ref` (the unmodified reference, pip-installed by `__graft_entry__.build()`; absent on boxes without
+    /root/reference and then skipped): the ln_prob composition that `bench.py --impl reference` times equals the oracle's
+    `ln_prob` on the headline model -- the same x87 arithmetic, bit for bit -- so either CPU arm measures the same work."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    ref = bench._reference_problem()
+    if ref is None:
+        pytest.skip('baseline/_ref not installed')
+    ln_prob, pset = ref
+    go, args, asimov, ps = bench._cpu_problem()
+    theta = bench.synth_theta(pset, 24, 77, sys.modules['models'])
+    theta[0, 0] = 1.5    # out of the prior box: -inf before any physics (llh.py:125-126)
+    for t in theta:
+        with np.errstate(all='ignore'):
+            try:
+                a = float(ln_prob(t))
+            except AssertionError:
+                a = np.nan
+            try:
+                b = float(go.ln_prob(list(t), args, asimov, ps))
+            except AssertionError:
+                b = np.nan
+        assert a == b or (a != a and b != b), (a, b)
+    assert float(ln_prob(theta[0])) == -np.inf
 
 
 def test_mcmc_driver_probes_scalar_callables(capsys):
