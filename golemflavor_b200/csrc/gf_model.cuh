@@ -47,7 +47,15 @@ struct gf_theta_view {
 /* Physical inputs of one parameter point. */
 struct gf_point {
     double sm[4], mass[2], np[4], loglam, src[3];
+    bool src_unit; /* the source sums to one by construction (SM-only path: no division by sum(source), see gf_point_fr) */
 };
+
+/* (sin^4 phi, cos 2psi) -> source composition.  Its entries sum to one -- sin^2 phi (cos^2 psi + sin^2 psi) + cos^2 phi --
+ * as long as sin^4 phi <= 1 (beyond, fr.py:101-113 takes |cos^2 phi| and the sum is 2 sin^2 phi - 1). */
+GF_HD void gf_source_from_angles(double sphi4, double c2psi, gf_point& q) {
+    gfp_angles_to_fr(sphi4, c2psi, q.src);
+    q.src_unit = sphi4 <= 1.0;
+}
 
 /*
  * Kernel specialisations (compile-time, chosen by the host from the model):
@@ -98,9 +106,19 @@ struct gf_point {
     ((SPEC) == GF_SPEC_SM6 ? 6 : (SPEC) == GF_SPEC_FIXED7 ? 7 : (SPEC) == GF_SPEC_FIXED12 ? 12 : (SPEC) == GF_SPEC_SM4 ? 4 : \
      (SPEC) == GF_SPEC_NPFREE11 ? 11 : (SPEC) == GF_SPEC_SM5X ? 5 : 0)
 
+/* Which dimensions carry a (truncated) Gaussian prior term, as a compile-time bit mask (bit k = dimension k), for the
+ * specialisations that are the reference's own parameter sets: examples/inference.ipynb (three LIMITEDGAUSS mixing
+ * coordinates, flat dcp, flat source angles) and scripts/fr.py:30-104 (the same four, two GAUSSIAN mass-squared
+ * differences, flat logLam).  The prior loop then has no per-dimension kind test at all -- the SM-only kernel is bound by
+ * its instruction count and the runtime tests were a tenth of it.  -1: kinds read from the model at run time.  A model
+ * in one of these column layouts but with other prior kinds is served by the corresponding runtime-layout specialisation
+ * (gf_model_spec). */
+#define GF_SPEC_STATIC_GMASK(SPEC) ((SPEC) == GF_SPEC_SM6 ? 0x07 : (SPEC) == GF_SPEC_FIXED7 ? 0x37 : -1)
+GF_HD int gf_model_gauss_mask(const gf_dev_model& m);
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m);
 GF_HD bool gf_model_has_fixed_source(const gf_dev_model& m);
 GF_HD int gf_model_spec(const gf_dev_model& m);
+GF_HD int gf_model_layout_spec(const gf_dev_model& m);
 
 /* the general case: runtime column map */
 template <int SPEC, class Get>
@@ -116,9 +134,10 @@ GF_HD void gf_resolve_point_mapped(const gf_dev_model& m, Get get, gf_point& q) 
         for (int k = 0; k < 4; ++k) q.np[k] = m.col_np[k] >= 0 ? get(m.col_np[k]) : m.fixed_np[k];
     }
     if (SPEC != GF_SPEC_SM) q.loglam = m.col_scale >= 0 ? get(m.col_scale) : m.fixed_loglam;
+    q.src_unit = false;
     if (GF_SPEC_IS_FIXED(SPEC) || GF_SPEC_IS_NPFREE(SPEC)) return; /* the source (and for FIXED the NP mixing) comes from the constant bank */
     if (m.col_src[0] >= 0) {
-        gfp_angles_to_fr(get(m.col_src[0]), get(m.col_src[1]), q.src);
+        gf_source_from_angles(get(m.col_src[0]), get(m.col_src[1]), q);
     } else if (m.col_src3[0] >= 0) {
         q.src[0] = get(m.col_src3[0]);
         q.src[1] = get(m.col_src3[1]);
@@ -128,6 +147,7 @@ GF_HD void gf_resolve_point_mapped(const gf_dev_model& m, Get get, gf_point& q) 
         q.src[0] = x;
         q.src[1] = 1.0 - x;
         q.src[2] = 0.0;
+        q.src_unit = true;
     } else {
         q.src[0] = m.fixed_src[0];
         q.src[1] = m.fixed_src[1];
@@ -138,12 +158,13 @@ GF_HD void gf_resolve_point_mapped(const gf_dev_model& m, Get get, gf_point& q) 
 /* Resolve theta columns / fixed values -> physical inputs (fr.py:421-435, llh notebook model). */
 template <int SPEC = GF_SPEC_GENERIC, class Get>
 GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
+    q.src_unit = false;
     if constexpr (SPEC == GF_SPEC_SM6) {
         q.sm[0] = get(0);
         q.sm[1] = get(1);
         q.sm[2] = get(2);
         q.sm[3] = get(3);
-        gfp_angles_to_fr(get(4), get(5), q.src);
+        gf_source_from_angles(get(4), get(5), q);
     } else if constexpr (SPEC == GF_SPEC_SM4) {
         q.sm[0] = get(0);
         q.sm[1] = get(1);
@@ -161,6 +182,7 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         q.src[0] = x;
         q.src[1] = 1.0 - x;
         q.src[2] = 0.0;
+        q.src_unit = true;
     } else if constexpr (SPEC == GF_SPEC_NPFREE11) {
         q.sm[0] = get(0);
         q.sm[1] = get(1);
@@ -344,14 +366,23 @@ template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class ThetaSrc
 GF_HD unsigned gf_point_fr(const gf_dev_model& m, const gf_point& q, double* fr, int lane = 0, const ThetaSrc& src = ThetaSrc()) {
     unsigned st = 0u;
     if (GF_SPEC_IS_SM(SPEC) || (SPEC == GF_SPEC_GENERIC && m.no_bsm)) {
-        double X[9];
-        gfp_pmns_abs2_coords(q.sm[0], q.sm[1], q.sm[2], q.sm[3], X);
-        double f[3];
-        gfp_mix(X, q.src[0], q.src[1], q.src[2], f);
-        const double inv = gfp_rcp(q.src[0] + q.src[1] + q.src[2]); /* fr.py:535 */
-        fr[0] = f[0] * inv;
-        fr[1] = f[1] * inv;
-        fr[2] = f[2] * inv;
+        /* fr = u_to_fr(source, angles_to_u(sm)) in the four independent entries of |U|^2.  A source built from the two
+         * source angles or from x sums to one by construction (q.src_unit): the division by sum(source) of fr.py:535
+         * is then a division by 1 +- 1 ulp and is not carried out; raw source ratios (config 1), fixed sources and
+         * source angles outside their natural box are normalised. */
+        const gfp_x4 x = gfp_pmns_abs2_coords4(q.sm[0], q.sm[1], q.sm[2], q.sm[3]);
+        const bool unit_sum = q.src_unit;
+        const double S = unit_sum ? 1.0 : q.src[0] + q.src[1] + q.src[2];
+        double f0, f1;
+        gfp_mix4(x, q.src[2], q.src[0] - q.src[2], q.src[1] - q.src[2], S, f0, f1);
+        if (!unit_sum) {
+            const double inv = gfp_rcp(S); /* fr.py:535 */
+            f0 *= inv;
+            f1 *= inv;
+        }
+        fr[0] = f0;
+        fr[1] = f1;
+        fr[2] = 1.0 - f0 - f1;
     } else if (!GF_SPEC_IS_SM(SPEC)) {
         /* the loop runs on the polynomial invariants of the pencil H0 + rho T; the matrices themselves are only needed
          * by the rare refinement path (see gf_mats_ptr / gf_mats_rebuild) */
@@ -449,13 +480,18 @@ GF_HD void gf_point_fr_scales(const gf_dev_model& m, const gf_point& q, int ns, 
     }
 }
 
+GF_HD int gf_model_gauss_mask(const gf_dev_model& m) {
+    int mask = 0;
+    for (int k = 0; k < m.ndim; ++k) mask |= (m.kind[k] != GF_PRIOR_UNIFORM) << k;
+    return mask;
+}
+
 GF_HD bool gf_model_has_fixed_source(const gf_dev_model& m) { return m.col_src[0] < 0 && m.col_x < 0 && m.col_src3[0] < 0; }
 
 GF_HD bool gf_model_is_fixed_spec(const gf_dev_model& m) { return !m.no_bsm && !m.np_free && gf_model_has_fixed_source(m); }
 
-/* which specialisation the host launches for a model (kernels without a GF_SPEC_NPFREE instance map it
- * to GF_SPEC_GENERIC) */
-GF_HD int gf_model_spec(const gf_dev_model& m) {
+/* the specialisation a model's COLUMN LAYOUT allows (kernels without a GF_SPEC_NPFREE instance map it to GF_SPEC_GENERIC) */
+GF_HD int gf_model_layout_spec(const gf_dev_model& m) {
     if (m.no_bsm) {
         const bool canon = m.ndim == 6 && m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3 &&
                            m.col_src[0] == 4 && m.col_src[1] == 5 && m.col_x < 0 && m.col_src3[0] < 0;
@@ -469,9 +505,18 @@ GF_HD int gf_model_spec(const gf_dev_model& m) {
     return GF_SPEC_FIXED;
 }
 
+/* which specialisation the log-posterior and sampler kernels launch: the layout's, unless it also fixes the prior kinds at
+ * compile time (GF_SPEC_STATIC_GMASK) and the model's differ -- then the runtime-layout sibling */
+GF_HD int gf_model_spec(const gf_dev_model& m) {
+    const int spec = gf_model_layout_spec(m);
+    if (spec == GF_SPEC_SM6 && gf_model_gauss_mask(m) != GF_SPEC_STATIC_GMASK(GF_SPEC_SM6)) return GF_SPEC_SM;
+    if (spec == GF_SPEC_FIXED7 && gf_model_gauss_mask(m) != GF_SPEC_STATIC_GMASK(GF_SPEC_FIXED7)) return GF_SPEC_FIXED;
+    return spec;
+}
+
 /* which specialisation the scan kernels launch: their own compile-time layouts where the model has one */
 GF_HD int gf_model_scan_spec(const gf_dev_model& m) {
-    const int spec = gf_model_spec(m);
+    const int spec = gf_model_layout_spec(m); /* the scans draw from the priors: no prior-kind specialisation */
     const bool sm03 = m.col_sm[0] == 0 && m.col_sm[1] == 1 && m.col_sm[2] == 2 && m.col_sm[3] == 3;
     if (spec == GF_SPEC_SM6) return GF_SPEC_SM;
     if (spec == GF_SPEC_SM) {
@@ -494,7 +539,7 @@ GF_HD int gf_model_scan_spec(const gf_dev_model& m) {
  * m.kind[k] is a constant-bank word and k a compile-time index, so the test runs on the uniform datapath and
  * saves three fp64-pipe instructions per uniform dimension; it also keeps an infinite coordinate inside an
  * unbounded box from turning into inf * 0 = NaN. */
-template <int NDIM = 0, class Get>
+template <int NDIM = 0, int GMASK = -1, class Get>
 GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
     double acc = 0.0;
     bool inside = true;
@@ -505,8 +550,8 @@ GF_HD double gf_point_lnprior(const gf_dev_model& m, Get get) {
     for (int k = 0; k < (NDIM > 0 ? NDIM : GF_MAX_DIM); ++k) {
         if (NDIM == 0 && k >= m.ndim) break;
         const double v = get(k);
-        inside = inside && (v >= m.lo[k]) && (v <= m.hi[k]);
-        if (m.kind[k] != GF_PRIOR_UNIFORM) {
+        inside = inside & (v >= m.lo[k]) & (v <= m.hi[k]); /* no short circuit: twelve chained compares, no branches */
+        if (GMASK >= 0 ? ((GMASK >> k) & 1) != 0 : m.kind[k] != GF_PRIOR_UNIFORM) {
             const double z = (v - m.mu[k]) * m.inv_sigma[k];
             acc = fma(z, z, acc);
         }
@@ -526,7 +571,7 @@ GF_HD double gf_multi_gaussian(const double* fr, const double* bf, double half_i
 /* llh.ln_prob (llh.py:121-130) with the Gaussian (or flat) likelihood. */
 template <int SPEC = GF_SPEC_GENERIC, int ILP = 1, int LANES = 1, class Get, class ThetaSrc = gf_no_src>
 GF_HD double gf_point_lnprob(const gf_dev_model& m, Get get, double* fr, unsigned& st, int lane = 0, const ThetaSrc& src = ThetaSrc()) {
-    const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC)>(m, get);
+    const double lp = gf_point_lnprior<GF_SPEC_STATIC_NDIM(SPEC), GF_SPEC_STATIC_GMASK(SPEC)>(m, get);
     GF_STAGE(3);
     if (!(lp > -INFINITY)) { /* -inf, or NaN from a NaN theta */
         fr[0] = fr[1] = fr[2] = NAN;

@@ -689,8 +689,11 @@ GF_HD void gfp_pmns_abs2(const gfp_trig& t, double* X) {
 
 /* |U_ai|^2 straight from the Haar-flat coordinates (s12^2, c13^4, s23^2, dcp): the squared sines and
  * cosines ARE the coordinates (fr.py:146-155 round-trips them through asin / sin), so the SM-only
- * models need two square roots -- c13^2 = sqrt(c13^4) and the interference term -- and cos(dcp) only. */
-GF_HD void gfp_pmns_abs2_coords(double s12_2, double c13_4, double s23_2, double dcp, double* X) {
+ * models need two square roots -- c13^2 = sqrt(c13^4) and the interference term -- and cos(dcp) only.
+ * |U|^2 is doubly stochastic, so only its four independent entries (rows e, mu; columns 1, 2 -- the layout
+ * of gfp_x4) are formed; gfp_mix4 writes the transition in them (9 + 14 fp64 instructions instead of 22 + 18
+ * for the nine entries and the full double sum: the SM-only kernel is bound by its instruction count). */
+GF_HD gfp_x4 gfp_pmns_abs2_coords4(double s12_2, double c13_4, double s23_2, double dcp) {
     const double c12_2 = 1.0 - s12_2, c23_2 = 1.0 - s23_2;
     const double c13_2 = gfp_sqrt01(c13_4), s13_2 = 1.0 - c13_2;
     /* 2 c23 s23 s12 c12 s13 cos(dcp); every factor is a non-negative root inside the prior box, a
@@ -698,15 +701,13 @@ GF_HD void gfp_pmns_abs2_coords(double s12_2, double c13_4, double s23_2, double
     const bool valid = s12_2 >= 0.0 && c12_2 >= 0.0 && s23_2 >= 0.0 && c23_2 >= 0.0 && s13_2 >= 0.0;
     const double prod = (c23_2 * s23_2) * (s12_2 * c12_2) * s13_2;
     const double cross = valid ? 2.0 * gfp_sqrt01(prod) * gfp_cos(dcp) : NAN;
-    X[0] = c13_2 * c12_2;
-    X[1] = c13_2 * s12_2;
-    X[2] = s13_2;
-    X[3] = fma(c23_2, s12_2, s23_2 * s13_2 * c12_2) + cross;
-    X[4] = fma(c23_2, c12_2, s23_2 * s13_2 * s12_2) - cross;
-    X[5] = s23_2 * c13_2;
-    X[6] = fma(s23_2, s12_2, c23_2 * s13_2 * c12_2) - cross;
-    X[7] = fma(s23_2, c12_2, c23_2 * s13_2 * s12_2) + cross;
-    X[8] = c23_2 * c13_2;
+    const double t = s23_2 * s13_2;
+    gfp_x4 x;
+    x.x00 = c13_2 * c12_2;                                  /* |U_e1|^2  */
+    x.x01 = c13_2 * s12_2;                                  /* |U_e2|^2  */
+    x.x10 = fma(c23_2, s12_2, t * c12_2) + cross;           /* |U_mu1|^2 */
+    x.x11 = fma(c23_2, c12_2, t * s12_2) - cross;           /* |U_mu2|^2 */
+    return x;
 }
 
 /* H = m1 u1 u1^+ + m2 u2 u2^+ for the columns above (U diag(0,m1,m2) U^+, fr.py:383-394). */
