@@ -106,15 +106,26 @@ GF_HD double gfp_rsqrt(double x) {
  * multiplication on top of the MUFU-seeded rsqrt instead of the ~12 fp64 instructions of the IEEE
  * routine; accurate to ~1 ulp.  Zero, tiny and out-of-domain arguments take the library path
  * (negative -> NaN like the reference's sqrt, fr.py:146-152). */
+#ifdef __CUDACC__
+/* the IEEE routine, out of line: its inlined body (Newton steps, a scaling branch, a call of its own) put two levels of
+ * divergence bookkeeping around every gfp_sqrt01 */
+static __device__ __noinline__ double gfp_sqrt_lib(double x) { return sqrt(x); }
+#endif
+
 GF_HD double gfp_sqrt01(double x) {
 #ifdef __CUDA_ARCH__
     /* 1e-290 < x < 1e290 tested on the exponent field with integer instructions (two fp64 compares would
      * sit on the pipe every kernel here is bound by): the unsigned subtraction sends negative numbers,
-     * zeros, subnormals, infinities and NaNs to the library path in one comparison */
+     * zeros, subnormals, infinities and NaNs to the library path in one comparison.  The fast value is computed
+     * unconditionally (garbage, never a trap, outside the range) and replaced on the rare path: the common path is the
+     * fall-through and pays one predicated branch. */
     const unsigned hi = (unsigned)__double2hiint(x);
-    if (hi - 0x03D00000u < 0x7C200000u - 0x03D00000u) return x * gfp_rsqrt(x); /* 2^-962 <= x < 2^963 */
-#endif
+    double r = x * gfp_rsqrt(x);
+    if (!(hi - 0x03D00000u < 0x7C200000u - 0x03D00000u)) r = gfp_sqrt_lib(x); /* outside 2^-962 <= x < 2^963 */
+    return r;
+#else
     return sqrt(x);
+#endif
 }
 
 /*
@@ -138,15 +149,29 @@ GF_HD double gfp_sqrt01(double x) {
 #define GFP_C5 2.08757232129817482790e-09
 #define GFP_C6 -1.13596475577881948265e-11
 
+#ifdef __CUDACC__
+/* 2/pi and the three-part split of -pi/2 (1.5707963267948966 + 6.123233995736757e-17 + 8.478427660368898e-32), in constant
+ * memory: a 64-bit literal costs two moves per use, a constant-bank word is a direct DFMA operand */
+static __constant__ double gfp_pio2_tab[4] = {0.63661977236758138, -1.5707963267948966, -6.123233995736757e-17, -8.478427660368898e-32};
+#endif
 #ifdef __CUDA_ARCH__
 /* r = x - k pi/2 with k = rint(x 2/pi); returns k */
 __device__ __forceinline__ int gfp_reduce_pio2(double x, double& r) {
-    const double kd = rint(x * 0.63661977236758138);
-    r = fma(kd, -__longlong_as_double(0x3ff921fb54442d18ll), x); /* pi/2 = 1.5707963267948966 + 6.123233995736757e-17 */
-    r = fma(kd, -__longlong_as_double(0x3c91a62633145c00ll), r); /*        + 8.478427660368898e-32 (three-part split) */
-    r = fma(kd, -__longlong_as_double(0x397b839a252049c0ll), r);
+    const double kd = rint(x * gfp_pio2_tab[0]);
+    r = fma(kd, gfp_pio2_tab[1], x);
+    r = fma(kd, gfp_pio2_tab[2], r);
+    r = fma(kd, gfp_pio2_tab[3], r);
     return (int)kd;
 }
+#endif
+
+#ifdef __CUDACC__
+/* Horner coefficients of gfp_cos by quadrant parity (row 0: cos r = 1 + z (-1/2 + z (C1 + ... + z C6)); row 1:
+ * sin r = r + r z (S1 + ... + z S6), led by a zero so that both rows take the same seven steps).  In constant memory
+ * the row is picked by ONE index: seven LDC.64 instead of fourteen FSEL plus the moves that materialise both
+ * coefficient sets -- a twentieth of the SM-only kernel's instructions. */
+static __constant__ double gfp_cos_tab[2][8] = {{GFP_C6, GFP_C5, GFP_C4, GFP_C3, GFP_C2, GFP_C1, -0.5, 0.0},
+                                                {0.0, GFP_S6, GFP_S5, GFP_S4, GFP_S3, GFP_S2, GFP_S1, 0.0}};
 #endif
 
 GF_HD void gfp_sincos(double x, double* sn, double* cs) {
@@ -158,8 +183,11 @@ GF_HD void gfp_sincos(double x, double* sn, double* cs) {
     double r;
     const int k = gfp_reduce_pio2(x, r);
     const double z = r * r;
-    const double ps = fma(fma(fma(fma(fma(GFP_S6, z, GFP_S5), z, GFP_S4), z, GFP_S3), z, GFP_S2), z, GFP_S1);
-    const double pc = fma(fma(fma(fma(fma(GFP_C6, z, GFP_C5), z, GFP_C4), z, GFP_C3), z, GFP_C2), z, GFP_C1);
+    /* coefficients as constant-bank operands (gfp_cos_tab, compile-time indices): a 64-bit literal is two moves per use */
+    const double* __restrict__ kc = gfp_cos_tab[0];
+    const double* __restrict__ ks = gfp_cos_tab[1];
+    const double ps = fma(fma(fma(fma(fma(ks[1], z, ks[2]), z, ks[3]), z, ks[4]), z, ks[5]), z, ks[6]);
+    const double pc = fma(fma(fma(fma(fma(kc[0], z, kc[1]), z, kc[2]), z, kc[3]), z, kc[4]), z, kc[5]);
     const double s = fma(r * z, ps, r);
     const double c = fma(z, fma(z, pc, -0.5), 1.0);
     /* quadrant: (sin, cos)(x) = (s, c), (c, -s), (-s, -c), (-c, s) for k mod 4 = 0..3 */
@@ -178,16 +206,15 @@ GF_HD double gfp_cos(double x) {
     double r;
     const int k = gfp_reduce_pio2(x, r);
     const double z = r * r;
-    /* one Horner chain with the coefficients selected by the quadrant parity:
-     * even k: cos r = 1 + z (-1/2 + z (C1 + ... + z C6));  odd k: sin r = r + r z (S1 + ... + z S6) */
     const bool odd = k & 1;
-    double p = odd ? 0.0 : GFP_C6;
-    p = fma(p, z, odd ? GFP_S6 : GFP_C5);
-    p = fma(p, z, odd ? GFP_S5 : GFP_C4);
-    p = fma(p, z, odd ? GFP_S4 : GFP_C3);
-    p = fma(p, z, odd ? GFP_S3 : GFP_C2);
-    p = fma(p, z, odd ? GFP_S2 : GFP_C1);
-    p = fma(p, z, odd ? GFP_S1 : -0.5);
+    const double* __restrict__ c = gfp_cos_tab[k & 1];
+    double p = c[0];
+    p = fma(p, z, c[1]);
+    p = fma(p, z, c[2]);
+    p = fma(p, z, c[3]);
+    p = fma(p, z, c[4]);
+    p = fma(p, z, c[5]);
+    p = fma(p, z, c[6]);
     const double v = fma(odd ? r * z : z, p, odd ? r : 1.0);
     /* cos x = c, -s, -c, s for k mod 4 = 0..3 */
     return ((k + 1) & 2) ? -v : v;

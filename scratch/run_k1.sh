@@ -8,5 +8,6 @@ GOLEMFLAVOR_B200_LIB=$v python scratch/k1_bench.py $O/k1_ref.npy 2>&1 | grep -v 
 GOLEMFLAVOR_B200_LIB=$v python scratch/k2_bench.py $O/k2_ref_r2.npy 2>&1 | grep -v Warn >> $O/k1_ab.log
 done
 python scratch/ens_bench.py >> $O/k1_ab.log 2>&1
+for m in texture anarchic; do python scratch/scan_bench.py 1e9 $m >> $O/k1_ab.log 2>&1; done
 python -m pytest tests -m gpu -q -x > $O/pytest_r2i.log 2>&1; tail -3 $O/pytest_r2i.log >> $O/k1_ab.log
 cat $O/k1_ab.log
