@@ -47,6 +47,13 @@ def lnprob(fm, theta, spec=-1, rebuild=False):
     return lnp, fr, st
 
 
+def model_spec(fm):
+    """(spec the log-posterior / sampler kernels launch, spec the column layout alone allows, Gaussian-dimension bit mask)."""
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(load().hh_model_spec(fm.ref, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
 def fr(fm, theta, spec=-1):
     th = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, fm.ndim)
     n = th.shape[0]

@@ -18,6 +18,16 @@
 /* spec < 0: choose like the library does (FIXED specialisation when the model is eligible) */
 static bool use_fixed(const gf_dev_model& d, int spec) { return spec < 0 ? gf_model_is_fixed_spec(d) : spec == GF_SPEC_FIXED; }
 
+/* which specialisation gf_lnprob / the sampler would launch for the model (layout AND prior kinds) */
+extern "C" int hh_model_spec(const gf_model* model, int* spec, int* layout_spec, int* gauss_mask) {
+    gf_dev_model d;
+    if (int rc = gf_build_dev_model(model, &d)) return rc;
+    *spec = gf_model_spec(d);
+    *layout_spec = gf_model_layout_spec(d);
+    *gauss_mask = gf_model_gauss_mask(d);
+    return 0;
+}
+
 extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, double* lnp, double* fr, uint8_t* st, int spec) {
     gf_dev_model d;
     if (int rc = gf_build_dev_model(model, &d)) return rc;
@@ -26,6 +36,11 @@ extern "C" int hh_lnprob(const gf_model* model, const double* theta, int64_t n, 
         auto get = [&](int k) { return theta[i * d.ndim + k]; };
         unsigned s = 0u;
         double f[3];
+        /* the compile-time layouts (and prior-kind masks) on request: the caller vouches for the model's layout */
+        if (spec == GF_SPEC_SM6) lnp[i] = gf_point_lnprob<GF_SPEC_SM6, 1>(d, get, f, s);
+        else if (spec == GF_SPEC_SM) lnp[i] = gf_point_lnprob<GF_SPEC_SM, 1>(d, get, f, s);
+        else if (spec == GF_SPEC_FIXED7) lnp[i] = gf_point_lnprob<GF_SPEC_FIXED7, 2>(d, get, f, s);
+        else
         lnp[i] = fixed ? gf_point_lnprob<GF_SPEC_FIXED, 2>(d, get, f, s) : gf_point_lnprob<GF_SPEC_GENERIC, 2>(d, get, f, s); /* as k_lnprob */
         if (fr) memcpy(fr + 3 * i, f, sizeof(f));
         if (st) st[i] = (uint8_t)s;

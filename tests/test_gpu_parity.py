@@ -274,6 +274,57 @@ def test_sm_only_column_layouts_agree(torch, golden):
     assert np.max(np.abs(a[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
 
 
+def test_prior_kind_specialisations_and_unnormalised_source_angles(torch, golden):
+    """(i) The compile-time column layouts also fix the reference's own prior kinds at compile time; the same layout with
+    other kinds must be served by the runtime-kind kernels with the right values (here: a Gaussian prior on dcp / flat
+    priors on everything, against the oracle's lnprior + likelihood).  (ii) The SM-only path skips u_to_fr's division by
+    sum(source) only while the source sums to one by construction: source angles beyond their natural box
+    (sin^4 phi > 1, evaluated by flux_averaged_BSMu without a prior) are normalised like fr.py:535."""
+    from golemflavor_b200.enums import PriorsCateg
+    from golemflavor_b200.param import Param, ParamSet
+    g = golden('ref_llh.npz')
+    rng = np.random.default_rng(41)
+    bf = go.angles_to_fr(g['asimov_angles'])
+
+    def oracle_lnprob(pset, theta, ref_fr):
+        lo, hi = np.array(pset.ranges).T
+        kind = [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in pset]
+        return go.batch_lnprior(theta, lo, hi, kind, list(pset.nominal_values), [p.std or 1.0 for p in pset]) + \
+            go.batch_multi_gaussian(ref_fr, bf, 0.02)
+
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    theta = models.draw_in_ranges(pset, 4000, rng)
+    ref_fr = go.batch_u_to_fr(np.array(go.batch_angles_to_fr(theta[:, 4:6])).astype(float), go.batch_angles_to_u(theta[:, :4])).astype(float)
+    variants = [ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std or 0.5,
+                                prior=PriorsCateg.GAUSSIAN if p.name == 'dcp' else p.prior, tag=p.tag) for p in pset]),
+                ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std, prior=None, tag=p.tag) for p in pset])]
+    for other in [pset] + variants:
+        got = llh.LnProb(args, asimov, other)(theta).cpu().numpy()
+        ref = oracle_lnprob(other, theta, ref_fr)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin) and fin.sum() > 100
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+    args3, asimov3, pset3 = models.bsm_model_c3(g['asimov_angles'])
+    th3 = models.draw_in_ranges(pset3, 4000, rng)
+    fr3 = truth.eigh_flux_averaged_fr(th3[:, :4], th3[:, 4:6], model.TEXTURE_ANGLES['OET'], th3[:, 6], 6, models.BINNING, args3.source_ratio)
+    flat3 = ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std, prior=None, tag=p.tag) for p in pset3])
+    for other in (pset3, flat3):
+        got = llh.LnProb(args3, asimov3, other)(th3).cpu().numpy()
+        ref = oracle_lnprob(other, th3, fr3)
+        fin = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), fin) and fin.sum() > 100
+        assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) < LLH_RTOL
+    # (ii) through gf_flux_averaged_fr in the canonical (packed, 128-bit loads) and in a permuted layout
+    theta[:2000, 4] = rng.uniform(1.0, 2.5, 2000)
+    ref_fr = np.array([np.asarray(go.u_to_fr(go.angles_to_fr(t[4:6]), go.angles_to_u(t[:4])), dtype=np.float64) for t in theta[::10]])
+    perm = [4, 0, 1, 5, 2, 3]
+    fa = fr.flux_averaged_BSMu(theta, args, -2.0, pset)
+    fb = fr.flux_averaged_BSMu(theta[:, perm], args, -2.0, ParamSet([pset[k] for k in perm]))
+    fa, fb = np.asarray(fa), np.asarray(fb)
+    assert np.abs(fa[::10] - ref_fr).max() < 1e-13 and np.array_equal(fa, fb)
+    assert np.abs(fa.sum(axis=1) - 1).max() < 1e-14
+
+
 def test_theta_memory_layouts_through_the_c_abi(torch, golden):
     """The compile-time column layouts pick their loads from the theta view: 128-bit loads for packed,
     16-byte aligned rows of an even length, scalar loads at constant offsets for contiguous rows, strided

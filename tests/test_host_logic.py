@@ -507,6 +507,62 @@ def test_harness_cubic_root_seeded_newton_is_full_precision():
     assert hh.cubic_w(np.array([0.0]))[0] == 0.0 and np.isnan(hh.cubic_w(np.array([np.nan]))[0])
 
 
+def test_harness_prior_kind_specialisations_and_their_fallback(golden):
+    """GF_SPEC_SM6 / GF_SPEC_FIXED7 fix the reference's own prior kinds at compile time (examples/inference.ipynb: three
+    LIMITEDGAUSS mixing coordinates, flat dcp and source angles; scripts/fr.py:30-104: the same four, two GAUSSIAN masses,
+    flat logLam).  On those models they give what the runtime-kind code gives; a model in the same column layout but with
+    other prior kinds is routed to the runtime-layout sibling (gf_model_spec), never to the wrong mask."""
+    SM, FIXED, SM6, FIXED7 = 2, 1, 4, 5          # GF_SPEC_* of gf_model.cuh
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    assert hh.model_spec(fm) == (SM6, SM6, 0b000111)
+    a = hh.lnprob(fm, g['theta'], spec=SM6)
+    b = hh.lnprob(fm, g['theta'], spec=SM)
+    c = hh.lnprob(fm, g['theta'])                # the generic specialisation
+    for x, y in ((a, b), (a, c)):
+        assert np.array_equal(x[0], y[0], equal_nan=True) and np.array_equal(x[1], y[1], equal_nan=True) and np.array_equal(x[2], y[2])
+    # same layout, dcp with a Gaussian prior: the mask differs, the layout does not
+    other = ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std or 0.5,
+                            prior=PriorsCateg.GAUSSIAN if p.name == 'dcp' else p.prior, tag=p.tag) for p in pset])
+    fo = model.flatten(args, asimov, other)
+    assert hh.model_spec(fo) == (SM, SM6, 0b001111)
+    ref = go.batch_lnprior(g['theta'], np.array(other.ranges)[:, 0], np.array(other.ranges)[:, 1],
+                           [0 if p.prior.name == 'UNIFORM' else 1 if p.prior.name == 'GAUSSIAN' else 2 for p in other],
+                           list(other.nominal_values), [p.std or 1.0 for p in other])
+    got = hh.lnprior(fo, g['theta'])
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin) and np.max(np.abs(got[fin] - ref[fin]) / np.maximum(1.0, np.abs(ref[fin]))) < 1e-12
+    # config 3 (scripts/fr.py layout)
+    args3, asimov3, pset3 = models.bsm_model_c3(g['asimov_angles'])
+    f3 = model.flatten(args3, asimov3, pset3)
+    assert hh.model_spec(f3) == (FIXED7, FIXED7, 0b0110111)
+    th = models.draw_in_ranges(pset3, 400, np.random.default_rng(3))
+    th[::7, 4] = 9e-23                           # out of the prior box
+    a = hh.lnprob(f3, th, spec=FIXED7)
+    b = hh.lnprob(f3, th, spec=FIXED)
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True) and np.array_equal(a[2], b[2])
+    flat = ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std, prior=None, tag=p.tag) for p in pset3])
+    assert hh.model_spec(model.flatten(args3, asimov3, flat)) == (FIXED, FIXED7, 0)
+
+
+def test_harness_source_angles_outside_their_natural_box(golden):
+    """fr.py:101-113 takes |cos^2 phi|: for sin^4 phi > 1 the source built from the angles no longer sums to one and
+    u_to_fr's division by sum(source) (fr.py:535) matters.  The SM-only path skips that division only while the source is
+    unit-sum by construction."""
+    g = golden('ref_llh.npz')
+    args, asimov, pset = models.notebook_model(g['asimov_angles'])
+    fm = model.flatten(args, asimov, pset)
+    rng = np.random.default_rng(11)
+    th = models.draw_in_ranges(pset, 200, rng)
+    th[:100, 4] = rng.uniform(1.0, 2.5, 100)     # sin^4 phi beyond one (no prior is evaluated by flux_averaged_fr)
+    th[100, 4], th[101, 4] = 1.0, 0.0
+    fr, st = hh.fr(fm, th)
+    ref = np.array([np.asarray(go.u_to_fr(go.angles_to_fr(t[4:6]), go.angles_to_u(t[:4])), dtype=np.float64) for t in th])
+    assert np.abs(fr - ref).max() < 1e-14 and np.abs(fr.sum(axis=1) - 1).max() < 1e-15
+    assert not st.any()
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on
     stdout with the contract's keys, timing the oracle port on the host cores; the GPU arm refuses to run
