@@ -46,16 +46,70 @@ enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 #ifndef GF_LP_PTS
 #define GF_LP_PTS 2
 #endif
-#define GF_LP_PTS_FOR(SPEC, KIND) ((GF_SPEC_IS_FIXED(SPEC) && (KIND) != GF_K_LNPRIOR) ? GF_LP_PTS : 1) /* the generic specialisation sits at the register limit already */
+/* The SM-only kernel in its packed compile-time layout (GF_SPEC_SM6, LAYOUT 2) runs ~260 instructions per point against 48 + 8
+ * bytes: a thread that loads its row, waits, computes and stores has nothing in flight for most of its life, and 32
+ * resident warps x 1.5 KB per SM are short of the ~47 KB per SM that ~1 us of latency at the HBM rate needs (long_scoreboard
+ * is its first stall reason, profiles/r02c_k1_sm_lnprob.md).  Each thread therefore loads the rows of GF_K1_PTS points into
+ * registers back to back before it evaluates the first one. */
+#ifndef GF_K1_PTS
+#define GF_K1_PTS 2
+#endif
+#define GF_LP_PTS_FOR(SPEC, KIND)                                                                                   \
+    (((KIND) == GF_K_LNPRIOR) ? 1 : GF_SPEC_IS_FIXED(SPEC) ? GF_LP_PTS : (SPEC) == GF_SPEC_SM6 ? GF_K1_PTS : 1) /* the generic specialisation sits at the register limit already */
 
 template <int KIND, int SPEC, int LAYOUT = 0>
 __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
-    constexpr int PTS = GF_LP_PTS_FOR(SPEC, KIND);
+    constexpr int PTS = GF_LP_PTS_FOR(SPEC, KIND); /* as in launch_lnprob */
     int64_t i = (int64_t)blockIdx.x * (blockDim.x * PTS) + threadIdx.x;
     if (i >= n) return;
-    if constexpr (PTS > 1) {
+    if constexpr (SPEC == GF_SPEC_SM6 && PTS > 1) {
+        /* all rows of this thread first (packed rows: 3 x 128-bit loads per point, 3 PTS loads in flight per thread), then
+         * the points one after the other from registers; rows past the end re-read the last row and are not evaluated */
+        constexpr int ND = GF_SPEC_STATIC_NDIM(SPEC);
+        double v[PTS][ND];
+#pragma unroll
+        for (int pt = 0; pt < PTS; ++pt) {
+            const int64_t j = i + (int64_t)pt * blockDim.x;
+            const double* __restrict__ r = th.p + (j < n ? j : n - 1) * th.ld_point;
+            if constexpr (LAYOUT == 2) {
+                const double2* __restrict__ r2 = reinterpret_cast<const double2*>(r);
+#pragma unroll
+                for (int k = 0; k < ND / 2; ++k) {
+                    const double2 t = __ldg(r2 + k);
+                    v[pt][2 * k] = t.x;
+                    v[pt][2 * k + 1] = t.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < ND; ++k) v[pt][k] = __ldg(r + (LAYOUT == 1 ? (int64_t)k : (int64_t)k * th.ld_dim));
+            }
+        }
+#pragma unroll
+        for (int pt = 0; pt < PTS; ++pt) {
+            const int64_t j = i + (int64_t)pt * blockDim.x;
+            if (j >= n) return;
+            double fr[3];
+            unsigned st = 0u;
+            const auto get = [&](int k) { return v[pt][k]; };
+            if (KIND == GF_K_FR) {
+                gf_point q;
+                gf_resolve_point<SPEC>(m, get, q);
+                st = gf_point_fr<SPEC, 1, 1>(m, q, fr);
+            } else {
+                lnp[j] = gf_point_lnprob<SPEC, 1, 1>(m, get, fr, st);
+            }
+            if (fr_out) {
+                fr_out[3 * j] = fr[0];
+                fr_out[3 * j + 1] = fr[1];
+                fr_out[3 * j + 2] = fr[2];
+            }
+            if (status) status[j] = (uint8_t)st;
+        }
+        return;
+    }
+    if constexpr (PTS > 1 && GF_SPEC_IS_FIXED(SPEC)) {
         if (LAYOUT != 0 || th.ld_dim == 1) { /* contiguous rows: one or two 32-byte sectors ahead of time */
             const int64_t nxt = i + blockDim.x;
             if (nxt < n) {
@@ -66,7 +120,7 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_L
         }
     }
 #pragma unroll 1
-    for (int pt = 0; pt < PTS; ++pt, i += blockDim.x) {
+    for (int pt = 0; pt < (GF_SPEC_IS_FIXED(SPEC) ? PTS : 1); ++pt, i += blockDim.x) {
     if (i >= n) return;
     const double* __restrict__ row = th.p + i * th.ld_point;
     /* the point: prior + physics + likelihood on whatever `get` reads theta from */
@@ -131,9 +185,9 @@ __global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_L
 template <int KIND>
 static void launch_lnprob(const gf_dev_model& d, int spec, const gf_theta_view& th, int64_t n, double* d_lnp, double* d_fr, uint8_t* d_status,
                           cudaStream_t stream) {
-    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS * GF_LP_PTS_FOR(spec, KIND));
     const bool rows = th.ld_dim == 1;
     const bool packed16 = rows && th.ld_point == d.ndim && (reinterpret_cast<uintptr_t>(th.p) & 15u) == 0;
+    const unsigned blocks = gf_blocks_for(n, GF_LP_THREADS * GF_LP_PTS_FOR(spec, KIND)); /* points per thread: as in k_lnprob */
 #define GF_LP_LAUNCH(SPEC, LAYOUT, SMEM) k_lnprob<KIND, SPEC, LAYOUT><<<blocks, GF_LP_THREADS, SMEM, stream>>>(d, th, n, d_lnp, d_fr, d_status)
     switch (spec) {
         case GF_SPEC_FIXED: GF_LP_LAUNCH(GF_SPEC_FIXED, 0, 0); break;

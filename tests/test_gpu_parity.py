@@ -299,7 +299,7 @@ def test_prior_kind_specialisations_and_unnormalised_source_angles(torch, golden
                                 prior=PriorsCateg.GAUSSIAN if p.name == 'dcp' else p.prior, tag=p.tag) for p in pset]),
                 ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std, prior=None, tag=p.tag) for p in pset])]
     for other in [pset] + variants:
-        got = llh.LnProb(args, asimov, other)(theta).cpu().numpy()
+        got = np.asarray(llh.LnProb(args, asimov, other)(theta))
         ref = oracle_lnprob(other, theta, ref_fr)
         fin = np.isfinite(ref)
         assert np.array_equal(np.isfinite(got), fin) and fin.sum() > 100
@@ -309,7 +309,7 @@ def test_prior_kind_specialisations_and_unnormalised_source_angles(torch, golden
     fr3 = truth.eigh_flux_averaged_fr(th3[:, :4], th3[:, 4:6], model.TEXTURE_ANGLES['OET'], th3[:, 6], 6, models.BINNING, args3.source_ratio)
     flat3 = ParamSet([Param(name=p.name, value=p.value, seed=p.seed, ranges=p.ranges, std=p.std, prior=None, tag=p.tag) for p in pset3])
     for other in (pset3, flat3):
-        got = llh.LnProb(args3, asimov3, other)(th3).cpu().numpy()
+        got = np.asarray(llh.LnProb(args3, asimov3, other)(th3))
         ref = oracle_lnprob(other, th3, fr3)
         fin = np.isfinite(ref)
         assert np.array_equal(np.isfinite(got), fin) and fin.sum() > 100
