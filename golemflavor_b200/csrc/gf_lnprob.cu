@@ -54,11 +54,14 @@ enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 #ifndef GF_K1_PTS
 #define GF_K1_PTS 2
 #endif
+#ifndef GF_K1_MIN_BLOCKS
+#define GF_K1_MIN_BLOCKS 18 /* resident 64-thread blocks per SM the SM-only kernels are compiled for (56 registers: no spill; 16: -2 %, 20 spills) */
+#endif
 #define GF_LP_PTS_FOR(SPEC, KIND)                                                                                   \
     (((KIND) == GF_K_LNPRIOR) ? 1 : GF_SPEC_IS_FIXED(SPEC) ? GF_LP_PTS : (SPEC) == GF_SPEC_SM6 ? GF_K1_PTS : 1) /* the generic specialisation sits at the register limit already */
 
 template <int KIND, int SPEC, int LAYOUT = 0>
-__global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? 16 : GF_LP_MIN_BLOCKS)
+__global__ void __launch_bounds__(GF_LP_THREADS, GF_SPEC_IS_SM(SPEC) ? (KIND == GF_K_LNPROB ? GF_K1_MIN_BLOCKS : 16) : GF_LP_MIN_BLOCKS)
     k_lnprob(const __grid_constant__ gf_dev_model m, const gf_theta_view th, const int64_t n, double* __restrict__ lnp,
              double* __restrict__ fr_out, uint8_t* __restrict__ status) {
     constexpr int PTS = GF_LP_PTS_FOR(SPEC, KIND); /* as in launch_lnprob */
