@@ -721,6 +721,32 @@ def test_reference_cardano_restatement_where_well_conditioned(torch):
     assert np.abs(got[good] - ref[good]).max() < FR_TOL
 
 
+def test_ragged_sizes_around_the_block_boundaries_of_the_multi_point_kernels(torch, golden):
+    """The compile-time-layout kernels evaluate two points per thread (rows i and i + 64 of a 128-point block; the SM-only
+    kernel loads both rows up front and re-reads the last row for a slot past the end): every n around the 64- and
+    128-point boundaries must give exactly the first n values of a larger batch, write nothing past n, and do so in every
+    theta view (packed rows, padded rows, column-major)."""
+    g = golden('ref_llh.npz')
+    lib = _lib.load()
+    rng = np.random.default_rng(77)
+    for args, asimov, pset in (models.notebook_model(g['asimov_angles']), models.bsm_model_c3(g['asimov_angles'])):
+        fn = llh.LnProb(args, asimov, pset)
+        nd = fn.ndim
+        theta = torch.as_tensor(models.draw_in_ranges(pset, 400, rng)).cuda()
+        full = fn(theta)
+        wide = torch.zeros((400, nd + 1), dtype=torch.float64, device='cuda')
+        wide[:, :nd] = theta
+        for n in (1, 2, 63, 64, 65, 127, 128, 129, 191, 193, 257):
+            soa = theta[:n].t().contiguous()
+            for ptr, ldp, ldd in ((theta, nd, 1), (wide, nd + 1, 1), (soa, 1, n)):
+                out = torch.full((n + 3,), 7.0, dtype=torch.float64, device='cuda')
+                frs = torch.full((n + 1, 3), 7.0, dtype=torch.float64, device='cuda')
+                st = torch.full((n + 1,), 255, dtype=torch.uint8, device='cuda')
+                _lib.check(lib.gf_lnprob(fn.model.ref, _lib.ptr(ptr), n, ldp, ldd, _lib.ptr(out), _lib.ptr(frs), _lib.ptr(st), _lib.stream_ptr(torch)))
+                assert torch.equal(out[:n], full[:n]) and bool((out[n:] == 7.0).all()), (nd, n, ldp, ldd)
+                assert bool((frs[n:] == 7.0).all()) and int(st[n]) == 255
+
+
 def test_layouts_devices_and_edge_cases(torch, golden):
     g = golden('ref_llh.npz')
     args, asimov, pset = models.notebook_model(g['asimov_angles'])
