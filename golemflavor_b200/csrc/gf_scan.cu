@@ -353,6 +353,230 @@ extern "C" int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells,
     return GF_OK;
 }
 
+/* ------------------------------------------------------------------ smoothed coverage region (plot.py:372-384, hist_smooth > 1/8 bin) */
+
+/*
+ * plot.flavor_contour smooths the normalised histogram with scipy.ndimage.gaussian_filter(H, sigma = hist_smooth) before it
+ * looks for the coverage region.  The default sigma = 0.05 bins truncates to a one-tap kernel (radius int(4 sigma + 1/2) = 0:
+ * the identity, served by the integer path above); any sigma >= 0.125 is a real separable filter.  One pass per axis with
+ * SciPy's own conventions -- boundary mode 'reflect' (d c b a | a b c d | d c b a), and for its symmetric kernels the
+ * accumulation order of ni_filters.c: centre tap first, then (left + right) pairs from the outside in, no FMA contraction
+ * -- so the smoothed field equals SciPy's bit for bit given the same weights (the caller passes SciPy's weights).
+ */
+#define GF_SMOOTH_MAX_RADIUS 64
+struct gf_smooth_weights {
+    double w[GF_SMOOTH_MAX_RADIUS + 1]; /* w[k] = weight at distance radius - k ... w[radius] = centre: SciPy's fw[0 .. size1] */
+};
+
+template <bool FROM_COUNTS>
+__global__ void __launch_bounds__(256) k_smooth_axis(const void* __restrict__ in_, double* __restrict__ out, int n1, int axis, int radius,
+                                                     const __grid_constant__ gf_smooth_weights W, double total) {
+    const int64_t cells = (int64_t)n1 * n1 * n1;
+    const int64_t stride = axis == 0 ? (int64_t)n1 * n1 : axis == 1 ? n1 : 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = (int)((i / stride) % n1);
+        const int64_t base = i - (int64_t)l * stride;
+        auto at = [&](int k) -> double { /* 'reflect': -1 -> 0, -2 -> 1, n -> n - 1, n + 1 -> n - 2, periodically for long kernels */
+            const int period = 2 * n1;
+            int m = k % period;
+            if (m < 0) m += period;
+            if (m >= n1) m = period - 1 - m;
+            const int64_t j = base + (int64_t)m * stride;
+            if (FROM_COUNTS) return __ddiv_rn((double)static_cast<const unsigned long long*>(in_)[j], total); /* H / np.sum(H) */
+            return static_cast<const double*>(in_)[j];
+        };
+        double tmp = __dmul_rn(at(l), W.w[radius]);
+        for (int ii = -radius; ii < 0; ++ii) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(at(l + ii), at(l - ii)), W.w[ii + radius]));
+        out[i] = tmp;
+    }
+}
+
+extern "C" int gf_hist_smooth(const unsigned long long* d_hist, int32_t n1, unsigned long long total, const double* h_weights, int32_t radius,
+                              double* d_out, double* d_work, void* stream) {
+    GF_REQUIRE(d_hist && d_out && d_work && h_weights, "gf_hist_smooth: null pointer");
+    GF_REQUIRE(n1 >= 1 && n1 <= 1024, "gf_hist_smooth: %d cells per axis outside [1, 1024]", n1);
+    GF_REQUIRE(radius >= 0 && radius <= GF_SMOOTH_MAX_RADIUS, "gf_hist_smooth: kernel radius %d outside [0, %d]", radius, GF_SMOOTH_MAX_RADIUS);
+    GF_REQUIRE(total > 0ull, "gf_hist_smooth: empty histogram");
+    gf_smooth_weights W;
+    for (int k = 0; k <= radius; ++k) W.w[k] = h_weights[k];
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    const int64_t cells = (int64_t)n1 * n1 * n1, want = (cells + 255) / 256;
+    const unsigned blocks = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    /* axes 0, 1, 2 in SciPy's order: counts -> out -> work -> out */
+    k_smooth_axis<true><<<blocks, 256, 0, st>>>(d_hist, d_out, n1, 0, radius, W, (double)total);
+    k_smooth_axis<false><<<blocks, 256, 0, st>>>(d_out, d_work, n1, 1, radius, W, 0.0);
+    k_smooth_axis<false><<<blocks, 256, 0, st>>>(d_work, d_out, n1, 2, radius, W, 0.0);
+    g_gf_launches += 3;
+    GF_LAUNCH_CHECK("gf_hist_smooth");
+    return GF_OK;
+}
+
+/*
+ * Coverage region of a non-negative float field (the smoothed histogram): the same definition and the same sort-free search
+ * as gf_coverage_mask.  Non-negative doubles order like their bit patterns, so the bisection runs on the 64-bit keys
+ * (at most 64 probes); G(c) = sum of the values with key > c is accumulated in double with a FIXED reduction tree (per-block
+ * partials summed in block order by the deciding thread): the same field gives the same mask on every run.
+ * wsd: [0] g  [1] total  [2] need;  wsu: as the integer path (counts of cells, keys)
+ */
+__global__ void __launch_bounds__(256) k_covf_reduce(const double* __restrict__ h, int64_t cells, const unsigned long long* __restrict__ wsu,
+                                                     double* __restrict__ part /*[gridDim.x][2]*/, unsigned long long* __restrict__ cnt /*[gridDim.x][3]*/) {
+    __shared__ double sg[8], stot[8];
+    __shared__ unsigned long long sn[8], se[8], smx[8];
+    const unsigned long long c = wsu[COV_PROBE], phase = wsu[COV_PHASE];
+    if (phase == 3ull) return;
+    double g = 0.0, tot = 0.0;
+    unsigned long long ngt = 0ull, eq = 0ull, mx = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = h[i];
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v > 0.0 ? v : 0.0); /* -0, NaN and negatives count as 0 */
+        g += key > c ? v : 0.0;
+        ngt += key > c ? 1ull : 0ull;
+        eq += key == c ? 1ull : 0ull;
+        mx = key > mx ? key : mx;
+        tot += v > 0.0 ? v : 0.0;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        g += __shfl_down_sync(0xffffffffu, g, o);
+        tot += __shfl_down_sync(0xffffffffu, tot, o);
+        ngt += __shfl_down_sync(0xffffffffu, ngt, o);
+        eq += __shfl_down_sync(0xffffffffu, eq, o);
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sg[warp] = g; stot[warp] = tot; sn[warp] = ngt; se[warp] = eq; smx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { g += sg[w]; tot += stot[w]; ngt += sn[w]; eq += se[w]; mx = smx[w] > mx ? smx[w] : mx; }
+        part[2 * blockIdx.x] = g; part[2 * blockIdx.x + 1] = tot;
+        cnt[3 * blockIdx.x] = ngt; cnt[3 * blockIdx.x + 1] = eq; cnt[3 * blockIdx.x + 2] = mx;
+    }
+}
+
+__global__ void k_covf_decide(unsigned long long* __restrict__ wsu, double* __restrict__ wsd, const double* __restrict__ part,
+                              const unsigned long long* __restrict__ cnt, int nblocks, double coverage_fraction) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long phase = wsu[COV_PHASE];
+    if (phase == 3ull) return;
+    double g = 0.0, tot = 0.0;
+    unsigned long long ngt = 0ull, eq = 0ull, mx = 0ull;
+    for (int b = 0; b < nblocks; ++b) { /* block order: a fixed summation tree */
+        g += part[2 * b]; tot += part[2 * b + 1];
+        ngt += cnt[3 * b]; eq += cnt[3 * b + 1]; mx = cnt[3 * b + 2] > mx ? cnt[3 * b + 2] : mx;
+    }
+    if (phase == 0ull) {
+        /* plot.py:381: searchsorted(cumsum(sorted H_s), coverage / 100) on the field itself (its sum is 1 up to rounding) */
+        wsd[1] = tot; wsd[2] = coverage_fraction;
+        wsu[COV_MAX] = mx;
+        if (!(tot > 0.0) || !(coverage_fraction > 0.0)) {
+            wsu[COV_CSTAR] = mx; wsu[COV_TAKE] = 0ull; wsu[COV_NGT_FINAL] = 0ull; wsu[COV_PHASE] = 3ull;
+            return;
+        }
+        wsu[COV_LO] = 0ull; /* G(key 0) = total: all positive cells */
+        wsu[COV_HI] = mx;
+        wsu[COV_PHASE] = 1ull;
+        if (!(tot >= coverage_fraction)) { /* the whole field holds less than the requested fraction: every positive cell is inside */
+            wsu[COV_CSTAR] = 0ull; wsu[COV_TAKE] = 0ull; wsu[COV_NGT_FINAL] = ngt; wsu[COV_PHASE] = 3ull;
+            return;
+        }
+    } else if (phase == 1ull) {
+        if (g < wsd[2]) wsu[COV_HI] = wsu[COV_PROBE]; else wsu[COV_LO] = wsu[COV_PROBE];
+    } else {
+        const unsigned long long ckey = wsu[COV_PROBE];
+        const double cstar = __longlong_as_double((long long)ckey), need = wsd[2];
+        unsigned long long m = 0ull; /* tied cells j = 1, 2, ... are inside while g + j c* < need */
+        if (cstar > 0.0) {
+            m = (unsigned long long)fmax(floor((need - g) / cstar), 0.0);
+            while (g + (double)(m + 1ull) * cstar < need) ++m;
+            while (m > 0ull && !(g + (double)m * cstar < need)) --m;
+        }
+        wsu[COV_CSTAR] = ckey;
+        wsu[COV_TAKE] = m < eq ? m : eq;
+        wsu[COV_NGT_FINAL] = ngt;
+        wsu[COV_PHASE] = 3ull;
+        wsd[0] = g;
+        return;
+    }
+    const unsigned long long lo = wsu[COV_LO], hi = wsu[COV_HI];
+    if (hi - lo > 1ull) {
+        wsu[COV_PROBE] = lo + (hi - lo) / 2ull;
+    } else {
+        wsu[COV_PROBE] = hi;
+        wsu[COV_PHASE] = 2ull;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_covf_mask(const double* __restrict__ h, int64_t cells, const unsigned long long* __restrict__ ws,
+                                                    uint8_t* __restrict__ mask) {
+    __shared__ unsigned int warp_ties[32];
+    __shared__ unsigned long long base;
+    const unsigned long long c = ws[COV_CSTAR], take = ws[COV_TAKE];
+    const bool nothing = ws[COV_NGT_FINAL] == 0ull && take == 0ull;
+    if (threadIdx.x == 0) base = 0ull;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t start = 0; start < cells; start += blockDim.x) {
+        const int64_t i = start + threadIdx.x;
+        const double v = i < cells ? h[i] : 0.0;
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v > 0.0 ? v : 0.0);
+        const bool tie = !nothing && i < cells && key == c && c > 0ull;
+        const unsigned ballot = __ballot_sync(0xffffffffu, tie);
+        if (lane == 0) warp_ties[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned before = __popc(ballot & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += warp_ties[w];
+        const unsigned long long rank = base + before;
+        if (i < cells) mask[i] = (!nothing && (key > c || (tie && rank < take))) ? 1 : 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned t = 0;
+            for (int w = 0; w < 32; ++w) t += warp_ties[w];
+            base += t;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int gf_coverage_mask_f64(const double* d_field, int64_t cells, double coverage_percent, uint8_t* d_mask, double* h_cstar,
+                                    unsigned long long* h_counts /*[2] or NULL*/, void* stream) {
+    GF_REQUIRE(cells >= 1 && d_field && d_mask, "gf_coverage_mask_f64: bad arguments");
+    GF_REQUIRE(coverage_percent >= 0.0 && coverage_percent <= 100.0, "gf_coverage_mask_f64: coverage = %g outside [0, 100]", coverage_percent);
+    cudaStream_t st = (cudaStream_t)stream;
+    int sms = 0;
+    if (int rc = gf_sm_count(&sms)) return rc;
+    const int64_t want = (cells + 255) / 256;
+    const int blocks = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    /* one stream-ordered allocation: integer state | double state | per-block partials */
+    const size_t bytes = (COV_WORDS + 4 + (size_t)blocks * 5) * 8;
+    unsigned long long* wsu = nullptr;
+    GF_CUDA(cudaMallocAsync(&wsu, bytes, st));
+    GF_CUDA(cudaMemsetAsync(wsu, 0, bytes, st));
+    double* wsd = reinterpret_cast<double*>(wsu + COV_WORDS);
+    double* part = wsd + 4;
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(part + 2 * (size_t)blocks);
+    for (int it = 0; it < 66; ++it) { /* first pass + <= 64 probes of the key bisection + the final probe; later ones are no-ops */
+        k_covf_reduce<<<blocks, 256, 0, st>>>(d_field, cells, wsu, part, cnt);
+        k_covf_decide<<<1, 32, 0, st>>>(wsu, wsd, part, cnt, blocks, coverage_percent / 100.0);
+        g_gf_launches += 2;
+    }
+    k_covf_mask<<<1, 1024, 0, st>>>(d_field, cells, wsu, d_mask);
+    ++g_gf_launches;
+    cudaError_t e = cudaGetLastError();
+    unsigned long long h[COV_WORDS] = {};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, wsu, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(wsu, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return gf_fail(GF_ERR_CUDA, "gf_coverage_mask_f64: %s", cudaGetErrorString(e));
+    if (h_cstar) memcpy(h_cstar, &h[COV_CSTAR], sizeof(double));
+    if (h_counts) {
+        h_counts[0] = h[COV_NGT_FINAL] + h[COV_TAKE];
+        h_counts[1] = h[COV_TAKE];
+    }
+    return GF_OK;
+}
+
 /* ------------------------------------------------------------------ Monte-Carlo evidence */
 
 __device__ __forceinline__ void gf_lse_merge(double& m, double& s, double m2, double s2) {

@@ -167,12 +167,54 @@ def ternary_histogram(frs, nb=25, return_tensor=False):
     return h if return_tensor else h.cpu().numpy()
 
 
-def coverage_mask(hist, coverage, return_tensor=False):
+def gaussian_weights(sigma, truncate=4.0):
+    """SciPy's normalised 1-D Gaussian kernel for ``gaussian_filter(sigma)`` (``scipy.ndimage._filters._gaussian_kernel1d``
+    with order 0): ``(radius, weights[-radius .. radius])`` with ``radius = int(truncate * sigma + 0.5)``."""
+    radius = int(truncate * float(sigma) + 0.5)
+    x = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (float(sigma) * float(sigma)) * x ** 2)
+    return radius, phi / phi.sum()
+
+
+def smooth_histogram(hist, hist_smooth, return_tensor=False):
+    """``H = H / np.sum(H); H_s = gaussian_filter(H, sigma=hist_smooth)`` of ``plot.flavor_contour`` (``plot.py:372-375``)
+    on the device, bit-identical to SciPy (separable, mode 'reflect', SciPy's accumulation order).  ``hist``: cubic
+    histogram of counts; returns float64 of the same shape."""
+    torch = _lib.torch_cuda()
+    h = hist.to(device='cuda', dtype=torch.int64).contiguous() if isinstance(hist, torch.Tensor) else \
+        torch.as_tensor(np.ascontiguousarray(hist, dtype=np.int64)).cuda()
+    n1 = int(h.shape[0])
+    if h.ndim != 3 or tuple(h.shape) != (n1, n1, n1):
+        raise ValueError('smooth_histogram: a cubic 3-D histogram is expected, got shape %s' % (tuple(h.shape),))
+    radius, w = gaussian_weights(hist_smooth)
+    total = int(h.sum().item())
+    out = torch.empty(h.shape, dtype=torch.float64, device='cuda')
+    work = torch.empty(h.shape, dtype=torch.float64, device='cuda')
+    wh = np.ascontiguousarray(w[:radius + 1], dtype=np.float64)        # outermost tap ... centre
+    _lib.check(_lib.load().gf_hist_smooth(_lib.ptr(h), n1, total, wh.ctypes.data_as(C.c_void_p), radius, _lib.ptr(out), _lib.ptr(work),
+                                          _lib.stream_ptr(torch)))
+    return out if return_tensor else out.cpu().numpy()
+
+
+def coverage_mask(hist, coverage, return_tensor=False, hist_smooth=0.05):
     """Highest-density region of a ternary histogram holding ``coverage`` per cent of the samples
     (``plot.flavor_contour``, ``plot.py:372-384``).  Returns ``(mask, info)``: ``mask`` has the shape of
     ``hist`` (1 inside the region); ``info = (content of the first excluded cell, number of masked
-    cells, number of masked cells tied with the first excluded one)``."""
+    cells, number of masked cells tied with the first excluded one)``.
+
+    ``hist_smooth`` is the reference's 3-D smoothing width in bins (``gaussian_filter(H, sigma=hist_smooth)``,
+    ``plot.py:375``).  Its default 0.05 -- like every value below 0.125 -- truncates to a one-tap kernel, the identity:
+    the region is then found on the integer counts.  Larger values filter the normalised histogram on the device
+    (``smooth_histogram``) and find the region on the smoothed field; ``info[0]`` is then a float."""
     torch = _lib.torch_cuda()
+    if gaussian_weights(hist_smooth)[0] > 0:
+        field = smooth_histogram(hist, hist_smooth, return_tensor=True)
+        mask = torch.empty(field.numel(), dtype=torch.uint8, device='cuda')
+        cstar, counts = C.c_double(), (C.c_uint64 * 2)()
+        _lib.check(_lib.load().gf_coverage_mask_f64(_lib.ptr(field), field.numel(), float(coverage), _lib.ptr(mask), C.byref(cstar), counts,
+                                                    _lib.stream_ptr(torch)))
+        mask = mask.reshape(field.shape)
+        return (mask if return_tensor else mask.cpu().numpy()), (float(cstar.value), int(counts[0]), int(counts[1]))
     if isinstance(hist, torch.Tensor):
         h = hist.to(device='cuda', dtype=torch.int64).contiguous()
     else:

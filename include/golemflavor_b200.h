@@ -222,6 +222,22 @@ int gf_scan_evidence_grid(const gf_model* model, const gf_scan_config* cfg, cons
 int gf_coverage_mask(const unsigned long long* d_hist, int64_t cells, double coverage_percent, uint8_t* d_mask,
                      unsigned long long* h_info /*[3] or NULL*/, void* stream);
 
+/* The smoothing step of the same function for hist_smooth values that are not the identity (plot.py:372-375:
+ * `H = H / np.sum(H); H_s = gaussian_filter(H, sigma=hist_smooth)`): d_out[n1^3] = the normalised histogram filtered along
+ * the three axes with SciPy's conventions (separable, boundary mode 'reflect', symmetric-kernel accumulation order of
+ * scipy.ndimage, no FMA contraction: bit-identical to SciPy for the same weights).  `h_weights[0..radius]` (host) are the
+ * normalised Gaussian weights from the outermost tap to the centre, radius = int(4 sigma + 0.5) <= 64 -- SciPy's
+ * `_gaussian_kernel1d(sigma, 0, radius)[:radius + 1]`; `total` = the sum of the counts; d_work[n1^3] is scratch. */
+int gf_hist_smooth(const unsigned long long* d_hist /*[n1^3]*/, int32_t n1, unsigned long long total, const double* h_weights,
+                   int32_t radius, double* d_out /*[n1^3]*/, double* d_work /*[n1^3]*/, void* stream);
+
+/* gf_coverage_mask for a non-negative float field (the smoothed histogram of gf_hist_smooth): mask of the cells that
+ * precede `searchsorted(cumsum(sorted descending), coverage/100)` (plot.py:377-384; the threshold is the absolute fraction
+ * coverage/100 of a field that sums to one).  *h_cstar (host, optional) = value of the first excluded cell, h_counts =
+ * {number of masked cells, number of masked cells tied with it}.  Deterministic (fixed reduction order).  Synchronises `stream`. */
+int gf_coverage_mask_f64(const double* d_field, int64_t cells, double coverage_percent, uint8_t* d_mask, double* h_cstar /*or NULL*/,
+                         unsigned long long* h_counts /*[2] or NULL*/, void* stream);
+
 /* ---- ensemble sampler --------------------------------------------------- */
 /*
  * Device-resident affine-invariant ensemble sampler: the stretch move of emcee's EnsembleSampler

@@ -1151,6 +1151,43 @@ def test_coverage_mask_matches_reference_definition(torch):
     assert np.array_equal(gaussian_filter(H, sigma=0.05), H)   # the reference's smoothing really is the identity
 
 
+def test_smoothed_coverage_region_matches_scipy_and_the_reference_definition(torch):
+    """hist_smooth beyond the one-tap identity (plot.py:372-384 with gaussian_filter(H, sigma=hist_smooth)): the device
+    filter equals SciPy's bit for bit (separable, mode 'reflect', its accumulation order), and the region found on the
+    smoothed field is the reference's `argsort / cumsum / searchsorted` set."""
+    from scipy.ndimage import gaussian_filter
+    fm = scan.scan_model('unitary', source_ratio=(1, 0, 0))
+    for nb, n in ((25, 1_000_000), (60, 300_000)):
+        hist, _ = scan.scan_histogram(fm, n, nb=nb, seed=5, distributed=False)
+        H = hist / np.sum(hist)
+        for sigma in (0.125, 0.4, 1.0, 3.0):
+            Hs = gaussian_filter(H, sigma=sigma)
+            got = scan.smooth_histogram(hist, sigma)
+            assert got.shape == Hs.shape and np.array_equal(got, Hs), (nb, sigma, float(np.abs(got - Hs).max()))
+            assert abs(got.sum() - 1.0) < 1e-12
+            Hr = np.ravel(Hs)
+            order = np.argsort(Hr)[::-1]
+            crs = np.cumsum(Hr[order])
+            for cov in (68.0, 90.0, 99.0, 0.0):
+                thres = int(np.searchsorted(crs, cov / 100.))
+                mask, (cstar, nmask, ntie) = scan.coverage_mask(hist, cov, hist_smooth=sigma)
+                m = mask.ravel()
+                # the cumulative sums of the two methods differ in their rounding: allow the boundary cell itself to move
+                assert abs(int(m.sum()) - thres) <= 1 and nmask == int(m.sum()), (nb, sigma, cov, int(m.sum()), thres)
+                if thres == 0:
+                    continue
+                assert np.all(m[Hr > cstar] == 1) and np.all(m[Hr < cstar] == 0)
+                assert abs(cstar - Hr[order[min(thres, len(Hr) - 1)]]) <= 1e-12 * Hr.max()
+                again, info = scan.coverage_mask(hist, cov, hist_smooth=sigma)
+                assert np.array_equal(again, mask) and info == (cstar, nmask, ntie)      # deterministic
+    # the default width stays on the integer path
+    a, ia = scan.coverage_mask(hist, 90.0)
+    b, ib = scan.coverage_mask(hist, 90.0, hist_smooth=0.05)
+    assert np.array_equal(a, b) and ia == ib and isinstance(ia[0], int)
+    with pytest.raises(ValueError):
+        scan.smooth_histogram(np.zeros((3, 4, 3), dtype=np.int64), 0.4)
+
+
 def test_scan_evidence_against_oracle(torch):
     """ln mean(L) over prior draws: device log-sum-exp vs the oracle's likelihood on the same draws."""
     from argparse import Namespace

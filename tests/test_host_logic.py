@@ -563,6 +563,19 @@ def test_harness_source_angles_outside_their_natural_box(golden):
     assert not st.any()
 
 
+def test_gaussian_weights_are_scipys():
+    """scan.gaussian_weights restates SciPy's kernel construction (the device filter is handed these weights): same radius
+    rule int(4 sigma + 0.5) and bit-identical values; the reference's default hist_smooth = 0.05 is a one-tap identity."""
+    from scipy.ndimage import _filters, gaussian_filter
+    for sigma in (0.05, 0.1249, 0.125, 0.4, 1.0, 2.5, 16.0):
+        radius, w = scan.gaussian_weights(sigma)
+        assert radius == int(4.0 * sigma + 0.5) and len(w) == 2 * radius + 1
+        assert np.array_equal(w, _filters._gaussian_kernel1d(sigma, 0, radius))
+    assert scan.gaussian_weights(0.05)[0] == 0
+    h = np.random.default_rng(1).random((5, 5, 5))
+    assert np.array_equal(gaussian_filter(h, sigma=0.05), h)
+
+
 def test_bench_reference_arm_prints_one_contract_line():
     """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly one JSON line on
     stdout with the contract's keys, timing the oracle port on the host cores; the GPU arm refuses to run
