@@ -152,6 +152,7 @@ GF_HD void gf_resolve_point_mapped(const gf_dev_model& m, Get get, gf_point& q) 
         q.src[0] = m.fixed_src[0];
         q.src[1] = m.fixed_src[1];
         q.src[2] = m.fixed_src[2];
+        q.src_unit = m.src_S == 1.0; /* a normalised fixed source ((1,2,0)/3, (1,0,0), ...): dividing by exactly 1 is the identity */
     }
 }
 
@@ -173,6 +174,7 @@ GF_HD void gf_resolve_point(const gf_dev_model& m, Get get, gf_point& q) {
         q.src[0] = m.fixed_src[0];
         q.src[1] = m.fixed_src[1];
         q.src[2] = m.fixed_src[2];
+        q.src_unit = m.src_S == 1.0; /* a normalised fixed source: dividing by exactly 1 is the identity */
     } else if constexpr (SPEC == GF_SPEC_SM5X) {
         q.sm[0] = get(0);
         q.sm[1] = get(1);
