@@ -46,7 +46,7 @@ enum { GF_K_LNPROB = 0, GF_K_FR = 1, GF_K_LNPRIOR = 2 };
 #ifndef GF_LP_PTS
 #define GF_LP_PTS 2
 #endif
-/* The SM-only kernel in its packed compile-time layout (GF_SPEC_SM6, LAYOUT 2) runs ~260 instructions per point against 48 + 8
+/* The SM-only kernel in its compile-time layout (GF_SPEC_SM6; every theta view) runs ~260 instructions per point against 48 + 8
  * bytes: a thread that loads its row, waits, computes and stores has nothing in flight for most of its life, and 32
  * resident warps x 1.5 KB per SM are short of the ~47 KB per SM that ~1 us of latency at the HBM rate needs (long_scoreboard
  * is its first stall reason, profiles/r02c_k1_sm_lnprob.md).  Each thread therefore loads the rows of GF_K1_PTS points into
