@@ -30,12 +30,24 @@ extern std::atomic<unsigned long long> g_gf_launches;
 #ifndef GF_SCAN_MIN_BLOCKS
 #define GF_SCAN_MIN_BLOCKS 2
 #endif
+/* The SM-only scans (unitary, x) are register-light (~50), but the 70 KB block-private histogram allows three blocks per SM:
+ * at 256 threads that is 24 warps per SM and the fixed-latency `wait` stall leads (profiles/r02c_hist_unitary.md).  Larger
+ * blocks share one histogram among more warps: 512 threads x 2 blocks = 32 warps per SM (unitary 6.36 -> 6.70e10, x 3.96 ->
+ * 4.20e10 samples/s; 384 x 3: 6.54 / 4.18).  Grids too fine for a shared-memory histogram (global atomics) keep 256 threads:
+ * larger blocks lose 4 % there. */
+#ifndef GF_SCAN_THREADS_SM
+#define GF_SCAN_THREADS_SM 512
+#endif
+#ifndef GF_SCAN_BLOCKS_SM
+#define GF_SCAN_BLOCKS_SM 2
+#endif
+#define GF_SCAN_THREADS_FOR(SPEC) (GF_SPEC_IS_SM(SPEC) ? GF_SCAN_THREADS_SM : GF_SCAN_THREADS)
 
 /* ------------------------------------------------------------------ kernels */
 
 /* Source of compositions: drawn samples (SCAN) or a given array (GIVEN). */
 template <bool SCAN, bool SMEM_HIST, int SPEC>
-__global__ void __launch_bounds__(GF_SCAN_THREADS, GF_SPEC_IS_SM(SPEC) ? 3 : GF_SCAN_MIN_BLOCKS) /* BSM: <= 128 registers, two 256-thread blocks (2 x 70 KB histograms) per SM; SM-only: three */
+__global__ void __launch_bounds__(GF_SCAN_THREADS_FOR(SPEC), GF_SPEC_IS_SM(SPEC) ? GF_SCAN_BLOCKS_SM : GF_SCAN_MIN_BLOCKS) /* BSM: <= 128 registers, two 256-thread blocks (2 x 70 KB histograms) per SM; SM-only: three larger ones */
     k_hist(const __grid_constant__ gf_dev_model m, const uint64_t seed, const uint64_t first_index, const uint64_t count,
            const double* __restrict__ fr_in, const int nb1, const double step, unsigned long long* __restrict__ hist,
            unsigned long long* __restrict__ accepted) {
@@ -140,24 +152,25 @@ int launch_hist(const char* fn, const gf_dev_model& d, uint64_t seed, uint64_t f
     auto kern_s = GF_HIST_KERNEL(true);
     auto kern_g = GF_HIST_KERNEL(false);
 #undef GF_HIST_KERNEL
+    const int threads = (SCAN && use_smem && GF_SPEC_IS_SM(spec)) ? GF_SCAN_THREADS_SM : GF_SCAN_THREADS; /* <= GF_SCAN_THREADS_FOR of the launched instance */
     int per_sm = 1;
     if (use_smem) {
         GF_CUDA(cudaFuncSetAttribute(kern_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_s, GF_SCAN_THREADS, smem));
+        GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_s, threads, smem));
     } else {
-        GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_g, GF_SCAN_THREADS, 0));
+        GF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern_g, threads, 0));
     }
     GF_REQUIRE(per_sm >= 1, "%s: kernel does not fit on an SM (smem %zu B)", fn, smem);
     for (uint64_t done = 0; done < count; done += kMaxPerLaunch) {
         const uint64_t cnt = (count - done < kMaxPerLaunch) ? count - done : kMaxPerLaunch;
-        uint64_t want = (cnt + GF_SCAN_THREADS - 1) / GF_SCAN_THREADS;
+        uint64_t want = (cnt + threads - 1) / threads;
         const uint64_t persistent = (uint64_t)sms * per_sm;
         const unsigned blocks = (unsigned)(want < persistent ? want : persistent);
         const double* frp = d_fr ? d_fr + 3 * done : nullptr;
         if (use_smem)
-            kern_s<<<blocks, GF_SCAN_THREADS, smem, stream>>>(d, seed, first + done, cnt, frp, nb1, step, d_hist, d_accepted);
+            kern_s<<<blocks, threads, smem, stream>>>(d, seed, first + done, cnt, frp, nb1, step, d_hist, d_accepted);
         else
-            kern_g<<<blocks, GF_SCAN_THREADS, 0, stream>>>(d, seed, first + done, cnt, frp, nb1, step, d_hist, d_accepted);
+            kern_g<<<blocks, threads, 0, stream>>>(d, seed, first + done, cnt, frp, nb1, step, d_hist, d_accepted);
         ++g_gf_launches;
         GF_LAUNCH_CHECK(fn);
     }
