@@ -1,7 +1,11 @@
-# SM-only scans + scan tests + sharding invariance on the final build (run under gpurun)
+# A/B of the deferred-refinement bin loop (run under gpurun)
 set -x
 O=gpurun_out
-rm -f $O/scan_ab.log
-python scratch/scan_bench.py 1e9 unitary,x >> $O/scan_ab.log 2>&1
-python -m pytest tests -m gpu -q -x -k "scan or hist or cli or smoke" > $O/pytest_scan.log 2>&1; tail -3 $O/pytest_scan.log >> $O/scan_ab.log
-cat $O/scan_ab.log
+rm -f $O/defer_ab.log
+for v in golemflavor_b200/lib/libgolemflavor_b200.so scratch/variants/lib_defer.so golemflavor_b200/lib/libgolemflavor_b200.so scratch/variants/lib_defer.so; do
+echo "== $v" >> $O/defer_ab.log
+GOLEMFLAVOR_B200_LIB=$v python scratch/k2_bench.py $O/k2_ref_r2.npy 2>&1 | grep -v Warn >> $O/defer_ab.log
+GOLEMFLAVOR_B200_LIB=$v python scratch/scan_bench.py 1e9 anarchic 2>&1 | grep "nb= 25" >> $O/defer_ab.log
+GOLEMFLAVOR_B200_LIB=$v python scratch/evid_bench.py 2>&1 | grep evidence >> $O/defer_ab.log
+done
+cat $O/defer_ab.log
